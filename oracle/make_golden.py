@@ -1,0 +1,278 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference Python in this container.
+
+    python -m oracle.make_golden
+
+TEST INFRASTRUCTURE ONLY.  Needs /root/reference (read-only, container only).  The vectors
+are committed so that the GPU box (which has no reference tree) can check the CUDA path and
+the C oracle against what the reference itself computes.  Third-party stand-ins used for
+``chamferdist._C`` / ``knn_cuda`` are described in oracle/ref_harness.py.
+"""
+from __future__ import annotations
+
+import math
+import os
+import pickle
+
+import numpy as np
+import torch
+
+from . import ref_harness as rh
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+REF = rh.REFERENCE_ROOT
+
+
+def flatten_tree(edge_index, paths_to_base, reverse_topo):
+    """dict-based tree of utils/kinematic_utils.py:151-198 -> (order, parent, edge) int32 arrays."""
+    P = len(reverse_topo)
+    order = np.array([int(p) for p in reverse_topo], np.int32)
+    parent = -np.ones(P, np.int32)
+    edge = -np.ones(P, np.int32)
+    for part, path in paths_to_base.items():
+        part = int(part)
+        if len(path) > 1:
+            par = int(path[1])
+            parent[part] = par
+            edge[part] = int(edge_index[f"{part}_{par}"])
+    return order, parent, edge
+
+
+def gen_nao(ref):
+    torch.manual_seed(0)
+    pcs64, parts = rh.load_nao()
+    res = pickle.load(open(f"{REF}/demo_data/pretrained/nao/base-2/result_14999.pkl", "rb"))
+    complete = torch.from_numpy(res["complete_pc_list"]).float()          # [10,4096,3]
+    assert np.array_equal(complete.numpy(), pcs64.astype(np.float32))
+    cano_idx = int(res["cano_idx"])
+    cano = torch.from_numpy(res["cano_pc"]).float()
+    pc_list = torch.from_numpy(res["pc_list"]).float()
+    assert torch.equal(cano, complete[cano_idx])
+    assert torch.equal(pc_list, torch.cat([complete[:cano_idx], complete[cano_idx + 1:]]))
+    cd = ref.chamfer.ChamferDistance()
+    out = {"complete_pc_list": complete.numpy(), "cano_idx": np.int64(cano_idx),
+           "gt_part": parts.astype(np.int16)}
+
+    # KAT-A: hard-label skin of the base-2 relaxation result + Chamfer both ways
+    pose = torch.from_numpy(res["pred_pose_list"]).float()
+    part = torch.from_numpy(res["pred_cano_part"]).long()
+    skinned = ref.model_utils.compute_pc_transform(cano, pose, part)
+    d_f, i_f = cd(skinned, pc_list, return_index=True)
+    d_b, i_b = cd(skinned, pc_list, reverse=True, return_index=True)
+    out.update(katA_pose=pose.numpy(), katA_part=part.numpy().astype(np.int16), katA_skinned_s16=skinned.numpy()[:, ::16],
+               katA_sum_fwd=np.float64(d_f.double().sum().item()), katA_sum_bwd=np.float64(d_b.double().sum().item()),
+               katA_idx_fwd=i_f.numpy().astype(np.int16), katA_idx_bwd=i_b.numpy().astype(np.int16),
+               katA_d_fwd=d_f.numpy(), katA_d_bwd=d_b.numpy())
+
+    # KAT-B: raw frames 0 <-> 1, bidirectional
+    tot, i01, i10 = cd(complete[0:1], complete[1:2], bidirectional=True, return_index=True)
+    out.update(katB_sum=np.float64(tot.double().sum().item()), katB_idx_fwd=i01.numpy().astype(np.int16),
+               katB_idx_bwd=i10.numpy().astype(np.int16), katB_total=tot.numpy())
+
+    # KAT-C: kinematic-2 checkpoint -> KinematicModel.forward -> recon_loss (+ grads)
+    ck = torch.load(f"{REF}/demo_data/pretrained/nao/kinematic-2/model.pth.tar", map_location="cpu",
+                    weights_only=False)
+    km = ref.model.KinematicModel(pose_len=pc_list.shape[0], seg_part=ck["seg_part"], cano_pc=ck["cano_pc"],
+                                  knn=ref.KNN(k=1, transpose_mode=True), edge_index=ck["edge_index"],
+                                  paths_to_base=ck["paths_to_base"], reverse_topo=ck["reverse_topo"])
+    km.load_state_dict(ck["state_dict"], strict=True)
+    assert torch.equal(ck["cano_pc"].float().cpu(), cano)
+    pc_trans, seg_part, trans_list = km(cano)
+    loss = ref.loss.recon_loss(pc_trans, pc_list, cd)
+    loss.backward()
+    order, parent, edge = flatten_tree(ck["edge_index"], ck["paths_to_base"], ck["reverse_topo"])
+    out.update(katC_axis=km.axis_list.detach().numpy(), katC_moment=km.moment_list.detach().numpy(),
+               katC_theta=km.theta_list.detach().numpy(), katC_seg_part=ck["seg_part"].cpu().numpy().astype(np.int16),
+               katC_order=order, katC_parent=parent, katC_edge=edge,
+               katC_trans_list=trans_list.detach().numpy(), katC_pc_trans_s16=pc_trans.detach().numpy()[:, ::16],
+               katC_loss=np.float64(loss.item()), katC_g_axis=km.axis_list.grad.numpy(),
+               katC_g_moment=km.moment_list.grad.numpy(), katC_g_theta=km.theta_list.grad.numpy(),
+               katC_seg_out=seg_part.numpy().astype(np.int16))
+
+    # KAT-D: base-2 checkpoint -> BaseModel.forward (gumbel weights captured) -> recon_loss (+ grads)
+    cb = torch.load(f"{REF}/demo_data/pretrained/nao/base-2/model.pth.tar", map_location="cpu", weights_only=False)
+    bm = ref.model.BaseModel(num_parts=20, pose_len=pc_list.shape[0])
+    bm.load_state_dict(cb["state_dict"], strict=False)
+    captured = {}
+    import torch.nn.functional as F
+    orig = F.gumbel_softmax
+
+    def capture(logits, tau=1.0, hard=False, **kw):
+        w = orig(logits, tau=tau, hard=hard, **kw)
+        captured["w"] = w
+        captured["logits"] = logits
+        return w
+
+    F.gumbel_softmax = capture
+    try:
+        torch.manual_seed(2)
+        pc_trans, seg_arg, trans_list = bm(cano, tau=1.0)
+    finally:
+        F.gumbel_softmax = orig
+    W = captured["w"]
+    W.retain_grad()
+    loss = ref.loss.recon_loss(pc_trans, pc_list, cd)
+    loss.backward()
+    Wd = W.detach()
+    hot = Wd.argmax(dim=1)
+    assert int((Wd != 0).sum()) == Wd.shape[0]
+    out.update(katD_6d=bm.proposal_6d.detach().numpy(), katD_t=bm.proposal_t.detach().numpy(),
+               katD_w0=bm.seg_head.model[0].weight.detach().numpy(), katD_b0=bm.seg_head.model[0].bias.detach().numpy(),
+               katD_w2=bm.seg_head.model[2].weight.detach().numpy(),
+               katD_hot=hot.numpy().astype(np.int8), katD_hotval=Wd.gather(1, hot[:, None])[:, 0].numpy(),
+               katD_logits_s16=captured["logits"].detach().numpy()[::16], katD_seg_argmax=seg_arg.numpy().astype(np.int8),
+               katD_pc_trans_s16=pc_trans.detach().numpy()[:, ::16], katD_trans_list=trans_list.detach().numpy(),
+               katD_loss=np.float64(loss.item()), katD_g_6d=bm.proposal_6d.grad.numpy(),
+               katD_g_t=bm.proposal_t.grad.numpy(), katD_g_W_s8=W.grad.numpy()[::8])
+    np.savez_compressed(os.path.join(OUT, "nao.npz"), **out)
+    print("nao.npz  katA", out["katA_sum_fwd"], out["katA_sum_bwd"], "katB", out["katB_sum"],
+          "katC", out["katC_loss"], "katD", out["katD_loss"])
+
+
+def gen_se3(ref):
+    g = torch.Generator().manual_seed(7)
+    B = 64
+    l = torch.randn(B, 3, generator=g)
+    l = l / l.norm(dim=1, keepdim=True) * (0.5 + torch.rand(B, 1, generator=g))    # un-normalised axes (Q17)
+    m = torch.randn(B, 3, generator=g) * 0.3
+    theta = (torch.rand(B, generator=g) * 2 - 1) * 2.5
+    d = (torch.rand(B, generator=g) * 2 - 1) * 0.2
+    # edge cases
+    theta[0] = 1e-6; d[0] = 0.13            # exactly eps: with-rot branch, prismatic-like
+    theta[1] = 5e-7; d[1] = 0.2             # no-rot branch ignores d
+    theta[2] = math.pi                      # |theta-pi|<eps -> no-rot
+    theta[3] = 0.005                        # clamp theta^2*|l|^2 at 1e-4
+    theta[4] = -0.004
+    theta[5] = 0.0
+    theta[6] = 1e-6; d[6] = 1e-6
+    l.requires_grad_(True); m.requires_grad_(True); theta.requires_grad_(True); d.requires_grad_(True)
+    expc = ref.screw_se3.screw_param_to_exponential_coordinates(l, m, theta, d)
+    M = ref.screw_se3.transform_from_exponential_coordinates(expc)
+    coef = torch.randn(B, 4, 4, generator=g)
+    (M * coef).sum().backward()
+    d6 = torch.randn(50, 6, generator=g)
+    d6[0] = torch.tensor([1., 0, 0, 0, 1, 0])
+    d6.requires_grad_(True)
+    R = ref.screw_se3.rotation_6d_to_matrix(d6)
+    coefR = torch.randn(50, 3, 3, generator=g)
+    (R * coefR).sum().backward()
+    np.savez_compressed(os.path.join(OUT, "se3.npz"), l=l.detach().numpy(), m=m.detach().numpy(),
+                        theta=theta.detach().numpy(), d=d.detach().numpy(), expc=expc.detach().numpy(),
+                        M=M.detach().numpy(), coef=coef.numpy(), g_l=l.grad.numpy(), g_m=m.grad.numpy(),
+                        g_theta=theta.grad.numpy(), g_d=d.grad.numpy(), d6=d6.detach().numpy(),
+                        R=R.detach().numpy(), coefR=coefR.numpy(), g_d6=d6.grad.numpy())
+    print("se3.npz", M.shape, R.shape)
+
+
+def gen_fk(ref):
+    """fk on a synthetic mixed revolute/prismatic tree (sapien-shaped, cfg4) with root pose."""
+    g = torch.Generator().manual_seed(11)
+    T, P = 6, 8
+    E = P - 1
+    # random tree: parent of part c (c>=1 in a shuffled labelling) is an earlier part
+    perm = torch.randperm(P, generator=g).tolist()
+    root = perm[0]
+    par = {perm[0]: None}
+    edge_index, k = {}, 0
+    import networkx as nx
+    G = nx.DiGraph()
+    G.add_node(root)
+    for i in range(1, P):
+        c = perm[i]
+        p = perm[int(torch.randint(0, i, (1,), generator=g))]
+        par[c] = p
+        edge_index[f"{c}_{p}"] = k
+        k += 1
+        G.add_edge(c, p)
+    paths_to_base = nx.shortest_path(G, target=root)
+    reverse_topo = list(reversed(list(nx.topological_sort(G))))
+    axis = torch.randn(E, 3, generator=g); axis = axis / axis.norm(dim=1, keepdim=True) * (0.6 + 0.6 * torch.rand(E, 1, generator=g))
+    moment = torch.randn(E, 3, generator=g) * 0.2
+    theta = (torch.rand(T, E, generator=g) * 2 - 1)
+    dist = (torch.rand(T, E, generator=g) * 2 - 1) * 0.1
+    jt = ["prismatic" if i % 3 == 1 else "revolute" for i in range(E)]
+    outs = {}
+    for tag, (dl, jtl) in {"plain": (None, None), "dist": (dist, None), "typed": (dist, jt)}.items():
+        a, mo, th = axis.clone().requires_grad_(True), moment.clone().requires_grad_(True), theta.clone().requires_grad_(True)
+        di = dl.clone().requires_grad_(True) if dl is not None else None
+        out = ref.kinematic_utils.fk(paths_to_base, reverse_topo, edge_index, a, mo, th, distance_list=di,
+                                     joint_type_list=jtl)
+        coef = torch.randn(T, P, 4, 4, generator=g)
+        (out * coef).sum().backward()
+        outs.update({f"{tag}_out": out.detach().numpy(), f"{tag}_coef": coef.numpy(), f"{tag}_g_axis": a.grad.numpy(),
+                     f"{tag}_g_moment": mo.grad.numpy(), f"{tag}_g_theta": th.grad.numpy()})
+        if di is not None and di.grad is not None:
+            outs[f"{tag}_g_dist"] = di.grad.numpy()
+    order, parent, edge = flatten_tree(edge_index, paths_to_base, reverse_topo)
+    np.savez_compressed(os.path.join(OUT, "fk.npz"), axis=axis.numpy(), moment=moment.numpy(), theta=theta.numpy(),
+                        dist=dist.numpy(), joint_type=np.array([2 if j == "prismatic" else 1 for j in jt], np.int32),
+                        order=order, parent=parent, edge=edge, **outs)
+    print("fk.npz", order, parent, edge)
+
+
+def gen_chamfer_small(ref):
+    g = torch.Generator().manual_seed(3)
+    cd = ref.chamfer.ChamferDistance()
+    out = {}
+    for tag, (B, N, M) in {"a": (3, 257, 300), "b": (5, 20, 20), "c": (1, 1, 7), "d": (2, 1000, 33)}.items():
+        src = torch.randn(B, N, 3, generator=g).requires_grad_(True)
+        tgt = torch.randn(B, M, 3, generator=g).requires_grad_(True)
+        d_f, i_f = cd(src, tgt, return_index=True)
+        d_b, i_b = cd(src, tgt, reverse=True, return_index=True)
+        wf = torch.rand(B, N, generator=g); wb = torch.rand(B, M, generator=g)
+        ((d_f * wf).sum() + (d_b * wb).sum()).backward()
+        out.update({f"{tag}_src": src.detach().numpy(), f"{tag}_tgt": tgt.detach().numpy(), f"{tag}_d_fwd": d_f.detach().numpy(),
+                    f"{tag}_i_fwd": i_f.numpy(), f"{tag}_d_bwd": d_b.detach().numpy(), f"{tag}_i_bwd": i_b.numpy(),
+                    f"{tag}_wf": wf.numpy(), f"{tag}_wb": wb.numpy(), f"{tag}_g_src": src.grad.numpy(),
+                    f"{tag}_g_tgt": tgt.grad.numpy()})
+    # exact ties: integer lattice points => many equal distances, lowest index must win
+    src = torch.randint(-2, 3, (2, 64, 3), generator=g).float()
+    tgt = torch.randint(-2, 3, (2, 96, 3), generator=g).float()
+    d_f, i_f = cd(src, tgt, return_index=True)
+    out.update(tie_src=src.numpy(), tie_tgt=tgt.numpy(), tie_d_fwd=d_f.numpy(), tie_i_fwd=i_f.numpy())
+    np.savez_compressed(os.path.join(OUT, "chamfer_small.npz"), **out)
+    print("chamfer_small.npz")
+
+
+def gen_flow(ref):
+    g = torch.Generator().manual_seed(5)
+    m, n, T = 500, 180, 3
+    knn = ref.KNN(k=3, transpose_mode=True)
+    out = {}
+    blended, masks, queries, refs, flows = [], [], [], [], []
+    for t in range(T):
+        q = torch.rand(m, 3, generator=g) * 0.6 - 0.3
+        r = q[torch.randperm(m, generator=g)[:n]] + 0.01 * torch.randn(n, 3, generator=g)
+        if t == 0:
+            r[:5] = q[:5]                      # zero distances -> 1e-10 clamp (flow_utils.py:160)
+        f = 0.05 * torch.randn(n, 3, generator=g)
+        if t == 1:
+            f = f * 0.001                      # tiny flows: mask decided by the 0.05 threshold
+        b, mk = ref.flow_utils.blend_anchor_motion(q, r, f, knn, return_mask=True)
+        blended.append(b); masks.append(mk); queries.append(q); refs.append(r); flows.append(f)
+    gt = torch.stack(blended); mask = torch.stack(masks)
+    pred = (gt + 0.02 * torch.randn(gt.shape, generator=g)).requires_grad_(True)
+    l_mse = ref.loss.flow_loss(gt, pred, flow_mask_list=mask, robust=False)
+    g_mse, = torch.autograd.grad(l_mse, pred)
+    l_hub = ref.loss.flow_loss(gt, pred, flow_mask_list=mask, robust=True)
+    g_hub, = torch.autograd.grad(l_hub, pred)
+    l_nomask = ref.loss.flow_loss(gt, pred)
+    np.savez_compressed(os.path.join(OUT, "flow.npz"), query=torch.stack(queries).numpy(), ref=torch.stack(refs).numpy(),
+                        flow=torch.stack(flows).numpy(), blended=gt.numpy(), mask=mask.numpy(),
+                        pred=pred.detach().numpy(), l_mse=np.float64(l_mse.item()), g_mse=g_mse.numpy(),
+                        l_hub=np.float64(l_hub.item()), g_hub=g_hub.numpy(), l_nomask=np.float64(l_nomask.item()))
+    print("flow.npz", mask.float().mean().item())
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    ref = rh.import_reference()
+    gen_chamfer_small(ref)
+    gen_se3(ref)
+    gen_fk(ref)
+    gen_flow(ref)
+    gen_nao(ref)
+
+
+if __name__ == "__main__":
+    main()
