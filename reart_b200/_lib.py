@@ -1,0 +1,79 @@
+"""ctypes binding of libreart_b200.so (include/reart_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing or a call fails the
+caller gets an exception.  Tensors are passed as raw device pointers on the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "csrc", "libreart_b200.so")
+
+_c_i64 = ctypes.c_int64
+_c_int = ctypes.c_int
+_vp = ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/reart_b200.h one to one
+SIGNATURES = {
+    "reart_version": (ctypes.c_char_p, []),
+    "reart_error_string": (ctypes.c_char_p, [_c_int]),
+    "reart_knn1_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i64]),
+    "reart_knn1_fwd": (_c_int, [_vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp, _c_i64, _vp]),
+    "reart_chamfer_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i64]),
+    "reart_chamfer_bidir_fwd": (_c_int, [_vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp, _vp, _vp, _c_i64, _vp]),
+    "reart_knn1_bwd": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp]),
+    "reart_chamfer_bidir_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp]),
+    "reart_fp32_probe": (_c_int, [_c_int, _c_int, _c_int, _vp, _vp, ctypes.POINTER(ctypes.c_double),
+                                  ctypes.POINTER(ctypes.c_double), _vp]),
+}
+
+_lib = None
+
+
+class ReartError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """Load the C-ABI library; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise ReartError(
+                f"{SO_PATH} not found: build it with `python -m reart_b200.build` "
+                "(reart_b200 has no CPU or PyTorch fallback)")
+        handle = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        raise ReartError(f"{what} failed: {lib().reart_error_string(code).decode()} ({code})")
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise ReartError("reart_b200 kernels need CUDA tensors (there is no CPU fallback); got a tensor on "
+                             f"{t.device}")
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)

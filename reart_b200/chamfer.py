@@ -1,0 +1,214 @@
+"""Drop-in for the reference's ``utils/chamfer.py`` on B200.
+
+Same public names, argument meaning, return arities and error behaviour as
+``/root/reference/utils/chamfer.py`` (``ChamferDistance`` :20-132, ``knn_points`` :212-286,
+``knn_gather`` :289-337), with the third-party ``chamferdist._C`` calls (:174, :206) replaced
+by the sm_100a kernels behind ``libreart_b200.so``.  The bidirectional case runs both searches
+in ONE launch and one fused backward instead of two of each.
+
+There is no CPU path: CPU tensors raise ``ReartError``.
+"""
+from __future__ import annotations
+
+import warnings
+from collections import namedtuple
+from typing import Optional, Union
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+_KNN = namedtuple("KNN", "dists idx knn")
+
+
+def _as_f32(t: torch.Tensor) -> torch.Tensor:
+    t = t if t.dtype == torch.float32 else t.float()
+    return t.contiguous()
+
+
+class _Knn1(Function):
+    """K=1 search; replaces ``_knn_points`` (utils/chamfer.py:135-209) for K == 1."""
+
+    @staticmethod
+    def forward(ctx, p1, p2):
+        _lib.require_cuda(p1, p2)
+        L = _lib.lib()
+        p1c, p2c = _as_f32(p1), _as_f32(p2)
+        B, P1, _ = p1c.shape
+        P2 = p2c.shape[1]
+        dists = torch.empty(B, P1, dtype=torch.float32, device=p1.device)
+        idx = torch.empty(B, P1, dtype=torch.int64, device=p1.device)
+        nbytes = L.reart_knn1_workspace_bytes(B, P1, P2)
+        ws = _lib.workspace(nbytes, p1.device)
+        with torch.cuda.device(p1.device):
+            _lib.check(L.reart_knn1_fwd(_lib.ptr(p1c), _lib.ptr(p2c), B, P1, P2, _lib.ptr(dists), _lib.ptr(idx),
+                                        _lib.ptr(ws), nbytes, _lib.stream_ptr()), "reart_knn1_fwd")
+        ctx.save_for_backward(p1c, p2c, idx)
+        ctx.in_dtypes = (p1.dtype, p2.dtype)
+        ctx.mark_non_differentiable(idx)
+        return dists[:, :, None], idx[:, :, None]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_dists, grad_idx):
+        p1, p2, idx = ctx.saved_tensors
+        L = _lib.lib()
+        B, P1, _ = p1.shape
+        P2 = p2.shape[1]
+        g = _as_f32(grad_dists[:, :, 0])
+        g1 = torch.empty_like(p1)
+        g2 = torch.empty_like(p2)
+        with torch.cuda.device(p1.device):
+            _lib.check(L.reart_knn1_bwd(_lib.ptr(p1), _lib.ptr(p2), _lib.ptr(idx), _lib.ptr(g), B, P1, P2,
+                                        _lib.ptr(g1), _lib.ptr(g2), _lib.stream_ptr()), "reart_knn1_bwd")
+        return g1.to(ctx.in_dtypes[0]), g2.to(ctx.in_dtypes[1])
+
+
+class _ChamferBidir(Function):
+    """Both K=1 searches of ``ChamferDistance.forward`` (utils/chamfer.py:78-94) in one launch."""
+
+    @staticmethod
+    def forward(ctx, src, tgt):
+        _lib.require_cuda(src, tgt)
+        L = _lib.lib()
+        s, t = _as_f32(src), _as_f32(tgt)
+        B, N, _ = s.shape
+        M = t.shape[1]
+        dev = s.device
+        d_f = torch.empty(B, N, dtype=torch.float32, device=dev)
+        i_f = torch.empty(B, N, dtype=torch.int64, device=dev)
+        d_b = torch.empty(B, M, dtype=torch.float32, device=dev)
+        i_b = torch.empty(B, M, dtype=torch.int64, device=dev)
+        nbytes = L.reart_chamfer_workspace_bytes(B, N, M)
+        ws = _lib.workspace(nbytes, dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.reart_chamfer_bidir_fwd(_lib.ptr(s), _lib.ptr(t), B, N, M, _lib.ptr(d_f), _lib.ptr(i_f),
+                                                 _lib.ptr(d_b), _lib.ptr(i_b), _lib.ptr(ws), nbytes,
+                                                 _lib.stream_ptr()), "reart_chamfer_bidir_fwd")
+        ctx.save_for_backward(s, t, i_f, i_b)
+        ctx.in_dtypes = (src.dtype, tgt.dtype)
+        ctx.mark_non_differentiable(i_f, i_b)
+        return d_f, d_b, i_f, i_b
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_f, g_b, _gi_f, _gi_b):
+        s, t, i_f, i_b = ctx.saved_tensors
+        L = _lib.lib()
+        B, N, _ = s.shape
+        M = t.shape[1]
+        g_f, g_b = _as_f32(g_f), _as_f32(g_b)
+        need_tgt = ctx.needs_input_grad[1]
+        gs = torch.empty_like(s)
+        gt = torch.empty_like(t) if need_tgt else None
+        with torch.cuda.device(s.device):
+            _lib.check(L.reart_chamfer_bidir_bwd(_lib.ptr(s), _lib.ptr(t), _lib.ptr(i_f), _lib.ptr(i_b),
+                                                 _lib.ptr(g_f), _lib.ptr(g_b), B, N, M, _lib.ptr(gs), _lib.ptr(gt),
+                                                 _lib.stream_ptr()), "reart_chamfer_bidir_bwd")
+        return gs.to(ctx.in_dtypes[0]), (gt.to(ctx.in_dtypes[1]) if need_tgt else None)
+
+
+class ChamferDistance(torch.nn.Module):
+    """Same contract as the reference module (utils/chamfer.py:20-132).
+
+    Returns PER-POINT squared distances (``reduction`` is validated then ignored);
+    ``bidirectional=True`` adds ``fwd[B,N] + bwd[B,M]`` element-wise (needs N == M, Q2).
+    """
+
+    def __init__(self):
+        super().__init__()
+
+    def forward(
+        self,
+        source_cloud: torch.Tensor,
+        target_cloud: torch.Tensor,
+        bidirectional: Optional[bool] = False,
+        reverse: Optional[bool] = False,
+        reduction: Optional[str] = "mean",
+        return_index: Optional[bool] = False,
+    ):
+        if not isinstance(source_cloud, torch.Tensor):
+            raise TypeError("Expected input type torch.Tensor. Got {} instead".format(type(source_cloud)))
+        if not isinstance(target_cloud, torch.Tensor):
+            raise TypeError("Expected input type torch.Tensor. Got {} instead".format(type(target_cloud)))
+        if source_cloud.device != target_cloud.device:
+            raise ValueError(
+                "Source and target clouds must be on the same device. "
+                f"Got {source_cloud.device} and {target_cloud.device}."
+            )
+        batchsize_source, lengths_source, dim_source = source_cloud.shape
+        batchsize_target, lengths_target, dim_target = target_cloud.shape
+        if batchsize_source != batchsize_target:
+            raise ValueError("Source and target pointclouds must have the same batchsize.")
+        if dim_source != dim_target:
+            raise ValueError("Source and target pointclouds must have the same dimensionality.")
+        if bidirectional and reverse:
+            warnings.warn("Both bidirectional and reverse set to True. bidirectional behavior takes precedence.")
+        if reduction != "sum" and reduction != "mean":
+            raise ValueError('Reduction must either be "sum" or "mean".')
+        if dim_source != 3:
+            raise ValueError("reart_b200 kernels are specialised for 3-D points (D == 3).")
+
+        if bidirectional:
+            d_f, d_b, i_f, i_b = _ChamferBidir.apply(source_cloud, target_cloud)
+            if return_index:
+                return d_f + d_b, i_f, i_b
+            return d_f + d_b
+        if reverse:
+            nn = knn_points(target_cloud, source_cloud, K=1)
+            if return_index:
+                return nn.dists[..., 0], nn.idx[..., 0]
+            return nn.dists[..., 0]
+        nn = knn_points(source_cloud, target_cloud, K=1)
+        if return_index:
+            return nn.dists[..., 0], nn.idx[..., 0]
+        return nn.dists[..., 0]
+
+
+def _check_full_lengths(lengths, P, name):
+    if lengths is None:
+        return
+    if lengths.numel() and not bool((lengths == P).all()):
+        raise NotImplementedError(
+            f"{name}: ragged clouds are not supported (the reference never passes non-full lengths, "
+            "utils/chamfer.py:51-58,272-275)")
+
+
+def knn_points(
+    p1: torch.Tensor,
+    p2: torch.Tensor,
+    lengths1: Union[torch.Tensor, None] = None,
+    lengths2: Union[torch.Tensor, None] = None,
+    K: int = 1,
+    version: int = -1,
+    return_nn: bool = False,
+    return_sorted: bool = True,
+):
+    """Same signature as utils/chamfer.py:212-286; K == 1 and D == 3 only (the hot path)."""
+    if p1.shape[0] != p2.shape[0]:
+        raise ValueError("pts1 and pts2 must have the same batch dimension.")
+    if p1.shape[2] != p2.shape[2]:
+        raise ValueError("pts1 and pts2 must have the same point dimension.")
+    if K != 1:
+        raise NotImplementedError("reart_b200.knn_points implements K == 1 (what the reference's Chamfer path uses)")
+    if p1.shape[2] != 3:
+        raise ValueError("reart_b200 kernels are specialised for 3-D points (D == 3).")
+    _check_full_lengths(lengths1, p1.shape[1], "lengths1")
+    _check_full_lengths(lengths2, p2.shape[1], "lengths2")
+    p1_dists, p1_idx = _Knn1.apply(p1, p2)
+    p2_nn = None
+    if return_nn:
+        p2_nn = knn_gather(p2, p1_idx, lengths2)
+    return _KNN(dists=p1_dists, idx=p1_idx, knn=p2_nn if return_nn else None)
+
+
+def knn_gather(x: torch.Tensor, idx: torch.Tensor, lengths: Union[torch.Tensor, None] = None):
+    """Same contract as utils/chamfer.py:289-337 (full lengths): x [N,M,U], idx [N,L,K] -> [N,L,K,U]."""
+    N, M, U = x.shape
+    _N, L, K = idx.shape
+    if N != _N:
+        raise ValueError("x and idx must have same batch dimension.")
+    idx_expanded = idx[:, :, :, None].expand(-1, -1, -1, U)
+    return x[:, :, None].expand(-1, -1, K, -1).gather(1, idx_expanded)

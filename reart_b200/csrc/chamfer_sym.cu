@@ -1,0 +1,196 @@
+// chamfer_sym.cu -- bidirectional K=1 search that evaluates every (a_i, b_j) distance ONCE and
+// feeds both directions (row min for a_i over B, column min for b_j over A).
+//
+// Replaces the two chamferdist._C.knn_points_idx calls of ChamferDistance.forward
+// (utils/chamfer.py:78-94).  d(a,b) = fma(dz,dz,fma(dy,dy,dx*dx)) is bit-symmetric in (a,b)
+// (dx -> -dx squares to the same value), so one evaluation serves both oracle searches exactly.
+//
+// Why: measured on B200 the FMA pipe and the issue port are the same resource for this loop
+// (packed FADD2/FMUL2/FFMA2 occupy two issue slots each, FMNMX one; profiles/r01_fp32_probes.md),
+// so a one-direction sweep costs 6 + 1 slots per pair = at most 57 % of FP32 peak.  Sharing the
+// distance costs 6 + 1 (row) + 1 (column) + ~0.1 slots per TWO directed pairs.
+//
+// Layout: thread (warp w, lane l) keeps R consecutive A points  i = qbase + (32 w + l) R + r  in
+// registers; B streams through shared memory exactly as in knn1.cu (TMA bulk ring).  Row side:
+// running min + 32-target chunk id (as knn1.cu).  Column side: per target the lane folds its R
+// distances (FMNMX), the warp folds lanes with one REDUX.MIN on the bit pattern, lane 0 stores the
+// warp's value into a per-warp shared array; after each tile the CTA reduces the 8 warp arrays and
+// merges into global keys with 64-bit atomicMin (dist_bits<<32 | column-chunk), where a column
+// chunk is the 32*R consecutive A points owned by one warp.  Indices are recovered by the
+// finalize re-scan (knn1.cu) with chunk sizes 32 (rows) and 32*R (columns).
+#include "common.cuh"
+#include "kernels.h"
+#include <algorithm>
+
+namespace reart {
+
+constexpr int kSymTileChunks = 16;
+constexpr int kSymTilePoints = kSymTileChunks * kChunk;      // 512
+constexpr int kSymTileBytes = kSymTilePoints * 12;           // 6144
+constexpr int kSymStages = 3;
+constexpr int kSymThreads = 256;
+constexpr int kSymWarps = kSymThreads / 32;
+
+template <int R>
+__global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // [stages][tile bytes] | [stages][warps][tile points] u32
+    unsigned* colmin = reinterpret_cast<unsigned*>(smem_raw + kSymStages * kSymTileBytes);
+    __shared__ __align__(8) uint64_t full_bar[kSymStages];
+
+    int item = blockIdx.x;
+    const int qb = item % p.qblocks;
+    item /= p.qblocks;
+    const int split = item % p.splits;
+    const int b = item / p.splits;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int QB = R * kSymThreads;
+    const int qbase = qb * QB;
+    const float* __restrict__ q = p.a + (int64_t)b * p.na * 3;
+
+    u64 QX[R], QY[R], QZ[R];
+    float best[R], prev[R];
+    unsigned bch[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = qbase + tid * R + r;
+        float x = INFINITY, y = INFINITY, z = INFINITY;          // out-of-range rows never win a column
+        if (i < p.na) { x = q[3 * i]; y = q[3 * i + 1]; z = q[3 * i + 2]; }
+        QX[r] = pack2(x, x); QY[r] = pack2(y, y); QZ[r] = pack2(z, z);
+        best[r] = INFINITY; prev[r] = INFINITY; bch[r] = 0u;
+    }
+
+    const int chunks_total = p.nb_pad / kChunk;
+    const int cps = (chunks_total + p.splits - 1) / p.splits;
+    const int chunk0 = split * cps;
+    const int nchunks = min(cps, chunks_total - chunk0);
+    const int ntiles = (nchunks + kSymTileChunks - 1) / kSymTileChunks;
+    const float* __restrict__ tp = p.b_packed + (int64_t)b * p.nb_pad * 3 + (int64_t)chunk0 * kChunk * 3;
+    u64* __restrict__ keys_col = p.keys_b + (int64_t)b * p.nb;
+    const unsigned colchunk_base = (unsigned)(qbase / (32 * R));
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kSymStages; ++s) mbar_init(&full_bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int k) {
+        const int st = k % kSymStages;
+        const int nch = min(kSymTileChunks, nchunks - k * kSymTileChunks);
+        const uint32_t bytes = (uint32_t)nch * kChunk * 12;
+        mbar_expect_tx(&full_bar[st], bytes);
+        tma_bulk_g2s(smem_raw + st * kSymTileBytes, tp + (int64_t)k * kSymTilePoints * 3, bytes, &full_bar[st]);
+    };
+    if (tid == 0) {
+        for (int k = 0; k < min(kSymStages, ntiles); ++k) issue(k);
+    }
+
+    for (int k = 0; k < ntiles; ++k) {
+        const int st = k % kSymStages;
+        mbar_wait(&full_bar[st], (uint32_t)((k / kSymStages) & 1));
+        const int nch = min(kSymTileChunks, nchunks - k * kSymTileChunks);
+        const float4* __restrict__ tile = reinterpret_cast<const float4*>(smem_raw + st * kSymTileBytes);
+        unsigned* __restrict__ cm_w = colmin + (st * kSymWarps + warp) * kSymTilePoints;
+        for (int c = 0; c < nch; ++c) {
+            const float4* __restrict__ cg = tile + c * (kChunk / 4 * 3);
+#pragma unroll
+            for (int g = 0; g < kChunk / 4; ++g) {
+                const float4 X = cg[3 * g], Y = cg[3 * g + 1], Z = cg[3 * g + 2];
+                const u64 X01 = pack2(X.x, X.y), X23 = pack2(X.z, X.w);
+                const u64 Y01 = pack2(Y.x, Y.y), Y23 = pack2(Y.z, Y.w);
+                const u64 Z01 = pack2(Z.x, Z.y), Z23 = pack2(Z.z, Z.w);
+                float c0, c1, c2, c3;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float a0, a1, a2, a3;
+                    unpack2(sqdist_pair(QX[r], QY[r], QZ[r], X01, Y01, Z01), a0, a1);
+                    unpack2(sqdist_pair(QX[r], QY[r], QZ[r], X23, Y23, Z23), a2, a3);
+                    best[r] = min3(best[r], a0, a1);
+                    best[r] = min3(best[r], a2, a3);
+                    if (r == 0) { c0 = a0; c1 = a1; c2 = a2; c3 = a3; }
+                    else { c0 = fminf(c0, a0); c1 = fminf(c1, a1); c2 = fminf(c2, a2); c3 = fminf(c3, a3); }
+                }
+                const unsigned m0 = __reduce_min_sync(0xffffffffu, __float_as_uint(c0));
+                const unsigned m1 = __reduce_min_sync(0xffffffffu, __float_as_uint(c1));
+                const unsigned m2 = __reduce_min_sync(0xffffffffu, __float_as_uint(c2));
+                const unsigned m3 = __reduce_min_sync(0xffffffffu, __float_as_uint(c3));
+                if (lane == 0) *reinterpret_cast<uint4*>(cm_w + c * kChunk + 4 * g) = make_uint4(m0, m1, m2, m3);
+            }
+            const unsigned gid = (unsigned)(chunk0 + k * kSymTileChunks + c);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (best[r] < prev[r]) bch[r] = gid;
+                prev[r] = best[r];
+            }
+        }
+        __syncthreads();                                   // tile consumed, per-warp column minima complete
+        if (tid == 0 && k + kSymStages < ntiles) issue(k + kSymStages);
+        // fold the 8 per-warp column arrays of this tile and merge into the global column keys
+        const int npts = nch * kChunk;
+        const int jbase = (chunk0 + k * kSymTileChunks) * kChunk;
+        for (int e = tid; e < npts; e += kSymThreads) {
+            const int j = jbase + e;
+            if (j < p.nb) {
+                unsigned m = colmin[(st * kSymWarps) * kSymTilePoints + e];
+                unsigned wbest = 0;
+#pragma unroll
+                for (int w = 1; w < kSymWarps; ++w) {
+                    const unsigned v = colmin[(st * kSymWarps + w) * kSymTilePoints + e];
+                    if (v < m) { m = v; wbest = (unsigned)w; }
+                }
+                const u64 key = ((u64)m << 32) | (u64)(colchunk_base + wbest);
+                if (p.qblocks == 1) keys_col[j] = key;
+                else atomicMin(&keys_col[j], key);
+            }
+        }
+        // colmin[st] is rewritten no earlier than tile k+kSymStages, i.e. after >= 1 further __syncthreads
+    }
+
+    u64* __restrict__ keys_row = p.keys_a + (int64_t)b * p.na;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = qbase + tid * R + r;
+        if (i < p.na) {
+            const u64 key = ((u64)__float_as_uint(best[r]) << 32) | (u64)bch[r];
+            if (p.splits == 1) keys_row[i] = key;
+            else atomicMin(&keys_row[i], key);
+        }
+    }
+}
+
+static int sym_choose_splits(int64_t B, int qblocks, int chunks_total) {
+    const int64_t want = 148 * 2 * 6;
+    const int64_t base = B * qblocks;
+    int s = (int)ceil_div(want, base > 0 ? base : 1);
+    const int max_s = std::max(1, chunks_total / (2 * kSymTileChunks));
+    return std::max(1, std::min(s, max_s));
+}
+
+template <int R>
+static int launch_sym_r(SymParams& p, cudaStream_t stream) {
+    p.qblocks = (int)ceil_div(p.na, R * kSymThreads);
+    p.splits = sym_choose_splits(p.B, p.qblocks, p.nb_pad / kChunk);
+    p.col_chunk_pts = 32 * R;
+    const int64_t items = (int64_t)p.B * p.qblocks * p.splits;
+    if (items <= 0) return kOk;
+    if (items > 0x7fffffff) return kErrUnsupported;
+    if (p.splits > 1 && !p.keys_preset &&
+        cudaMemsetAsync(p.keys_a, 0xff, sizeof(u64) * (size_t)p.B * p.na, stream) != cudaSuccess)
+        return kErrLaunch;
+    if (p.qblocks > 1 && !p.keys_preset &&
+        cudaMemsetAsync(p.keys_b, 0xff, sizeof(u64) * (size_t)p.B * p.nb, stream) != cudaSuccess)
+        return kErrLaunch;
+    const size_t smem = (size_t)kSymStages * kSymTileBytes + (size_t)kSymStages * kSymWarps * kSymTilePoints * 4;
+    if (cudaFuncSetAttribute(chamfer_sym_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return kErrLaunch;
+    chamfer_sym_kernel<R><<<(unsigned)items, kSymThreads, smem, stream>>>(p);
+    REART_CHECK_LAUNCH();
+    return kOk;
+}
+
+int launch_chamfer_sym(SymParams& p, cudaStream_t stream) { return launch_sym_r<8>(p, stream); }
+
+}  // namespace reart

@@ -1,0 +1,117 @@
+// common.cuh -- shared device helpers for the reart_b200 sm_100a kernels.
+//
+// PTX wrappers used across kernels: packed f32x2 arithmetic (Blackwell FADD2/FMUL2/FFMA2),
+// 3-input min (FMNMX3), mbarrier + 1-D TMA bulk copy (UBLKCP).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace reart {
+
+typedef unsigned long long u64;
+
+// ----------------------------------------------------------------------------- error codes (include/reart_b200.h)
+enum : int {
+    kOk = 0,
+    kErrInvalidArg = -1,
+    kErrWorkspace = -2,
+    kErrLaunch = -3,
+    kErrUnsupported = -4,
+};
+
+#define REART_CHECK_LAUNCH()                                   \
+    do {                                                       \
+        cudaError_t e__ = cudaGetLastError();                  \
+        if (e__ != cudaSuccess) return reart::kErrLaunch;      \
+    } while (0)
+
+// ----------------------------------------------------------------------------- packed f32x2
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {
+    float m;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(m) : "f"(a), "f"(b), "f"(c));
+    return m;
+}
+
+// Squared distance in the pinned contraction order (oracle/reart_oracle.c sqdist3):
+//   d = fma(dz,dz, fma(dy,dy, dx*dx)),  dx = q.x - t.x
+__device__ __forceinline__ float sqdist_scalar(float qx, float qy, float qz, float tx, float ty, float tz) {
+    float dx = __fsub_rn(qx, tx), dy = __fsub_rn(qy, ty), dz = __fsub_rn(qz, tz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+// Two targets at once for one query (query operand is a scalar broadcast: FADD2 Rq.F32, -Rt.F32x2)
+__device__ __forceinline__ u64 sqdist_pair(u64 QX, u64 QY, u64 QZ, u64 TX, u64 TY, u64 TZ) {
+    u64 dx = sub2(QX, TX), dy = sub2(QY, TY), dz = sub2(QZ, TZ);
+    return fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+}
+
+// ----------------------------------------------------------------------------- mbarrier + TMA bulk copy
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk async copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__host__ __device__ __forceinline__ int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+__host__ __device__ __forceinline__ int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ----------------------------------------------------------------------------- packed cloud layout
+// A cloud [B,P,3] is re-laid out for the NN search as groups of 4 points
+//   [x0 x1 x2 x3 | y0 y1 y2 y3 | z0 z1 z2 z3]   (48 bytes, three float4)
+// padded with +INF coordinates to a multiple of kChunk points per batch element.
+constexpr int kChunk = 32;               // points per arg-min chunk (and padding granule)
+constexpr int kGroupFloats = 12;         // floats per group of 4 points
+
+__host__ __device__ __forceinline__ int64_t padded_points(int64_t P) { return round_up(P > 0 ? P : 1, kChunk); }
+__host__ __device__ __forceinline__ int64_t packed_floats_per_batch(int64_t P) { return padded_points(P) * 3; }
+
+}  // namespace reart

@@ -1,0 +1,269 @@
+// knn1.cu -- K=1 brute-force nearest-neighbour search, D=3, for sm_100a.
+//
+// Replaces chamferdist._C.knn_points_idx as the reference calls it (utils/chamfer.py:174,
+// K=1, via ChamferDistance.forward utils/chamfer.py:78-94).  Bit-exact with
+// oracle/reart_oracle.c:oracle_knn1 (d = fma(dz,dz,fma(dy,dy,dx*dx)), lowest index on ties).
+//
+// Design (see DESIGN.md "knn1"):
+//   * targets are re-laid out once per call into groups of 4 points [x0..x3|y0..y3|z0..z3]
+//     (pack kernel) so a tile is one contiguous byte range -> staged into shared memory by
+//     1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) through a 3-stage mbarrier ring;
+//   * each thread owns R queries in registers and sweeps the tile with packed f32x2 math:
+//     per 2 pairs 3 FADD2 + 1 FMUL2 + 2 FFMA2 (FMA pipe) + 1 FMNMX3 (ALU pipe);
+//   * no per-pair arg-min bookkeeping: only the running min is kept; every 32 targets
+//     ("chunk") a compare records which chunk last improved it.  The exact index is
+//     recovered afterwards by re-scanning that single chunk (finalize kernel);
+//   * work items (direction, batch, query block, target split) map 1:1 to CTAs; partial
+//     results merge with one 64-bit atomicMin per query on key = dist_bits<<32 | chunk
+//     (distances are >= 0 so their bit patterns order like the floats; the chunk id in the
+//     low word makes the lowest chunk win exact ties).
+#include "common.cuh"
+#include "kernels.h"
+#include <algorithm>
+
+namespace reart {
+
+constexpr int kTileChunks = 16;                              // chunks per smem stage
+constexpr int kTilePoints = kTileChunks * kChunk;            // 512 targets
+constexpr int kTileBytes = kTilePoints * 12;                 // 6144 B
+constexpr int kStages = 3;
+constexpr int kGroupsPerChunk = kChunk / 4;                  // 8
+
+// ----------------------------------------------------------------------------- pack
+// pts [B,P,3] -> packed [B, padded_points(P)/4, 12], +INF padded.  One thread per group.
+__global__ void pack_cloud_kernel(const float* __restrict__ pts, float* __restrict__ packed, int64_t B, int64_t P) {
+    const int64_t groups_per_b = padded_points(P) / 4;
+    const int64_t total = B * groups_per_b;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = g / groups_per_b, gi = g - b * groups_per_b;
+        float v[12];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t i = gi * 4 + k;
+            const bool ok = i < P;
+            const float* s = pts + (b * P + (ok ? i : 0)) * 3;
+            v[k] = ok ? s[0] : INFINITY;
+            v[4 + k] = ok ? s[1] : INFINITY;
+            v[8 + k] = ok ? s[2] : INFINITY;
+        }
+        float4* o = reinterpret_cast<float4*>(packed + g * kGroupFloats);
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+        o[2] = make_float4(v[8], v[9], v[10], v[11]);
+    }
+}
+
+int launch_pack_cloud(const float* pts, float* packed, int64_t B, int64_t P, cudaStream_t stream) {
+    if (B <= 0) return kOk;
+    const int64_t total = B * (padded_points(P) / 4);
+    const int threads = 256;
+    const int blocks = (int)(int64_t)std::min<int64_t>(ceil_div(total, threads), 148 * 8);
+    pack_cloud_kernel<<<blocks, threads, 0, stream>>>(pts, packed, B, P);
+    REART_CHECK_LAUNCH();
+    return kOk;
+}
+
+// ----------------------------------------------------------------------------- main search
+template <int R, int THREADS>
+__global__ void __launch_bounds__(THREADS, (R <= 8 && THREADS <= 256) ? 2 : 1) knn1_main_kernel(const KnnParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* tiles = reinterpret_cast<float4*>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+
+    // ---- decode work item: qb fastest so that neighbouring CTAs stream the same targets (L2 reuse)
+    int item = blockIdx.x;
+    int dir = 0;
+    if (item >= p.items0) { dir = 1; item -= p.items0; }
+    const KnnDir& D = p.dir[dir];
+    const int qb = item % D.qblocks;
+    item /= D.qblocks;
+    const int split = item % D.splits;
+    const int b = item / D.splits;
+
+    const int tid = threadIdx.x;
+    const int qbase = qb * (R * THREADS);
+    const float* __restrict__ q = D.q + (int64_t)b * D.nq * 3;
+
+    u64 QX[R], QY[R], QZ[R];
+    float best[R], prev[R];
+    unsigned bch[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = qbase + r * THREADS + tid;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (i < D.nq) { x = q[3 * i]; y = q[3 * i + 1]; z = q[3 * i + 2]; }
+        QX[r] = pack2(x, x); QY[r] = pack2(y, y); QZ[r] = pack2(z, z);
+        best[r] = INFINITY; prev[r] = INFINITY; bch[r] = 0u;
+    }
+
+    // ---- target chunk range of this split
+    const int chunks_total = D.nt_pad / kChunk;
+    const int cps = (chunks_total + D.splits - 1) / D.splits;
+    const int chunk0 = split * cps;
+    const int nchunks = min(cps, chunks_total - chunk0);
+    const int ntiles = (nchunks + kTileChunks - 1) / kTileChunks;
+    const float* __restrict__ tp = D.tpacked + (int64_t)b * D.nt_pad * 3 + (int64_t)chunk0 * kChunk * 3;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int k) {
+        const int st = k % kStages;
+        const int nch = min(kTileChunks, nchunks - k * kTileChunks);
+        const uint32_t bytes = (uint32_t)nch * kChunk * 12;
+        mbar_expect_tx(&full_bar[st], bytes);
+        tma_bulk_g2s(smem_raw + st * kTileBytes, tp + (int64_t)k * kTilePoints * 3, bytes, &full_bar[st]);
+    };
+    if (tid == 0) {
+        for (int k = 0; k < min(kStages, ntiles); ++k) issue(k);
+    }
+
+    for (int k = 0; k < ntiles; ++k) {
+        const int st = k % kStages;
+        mbar_wait(&full_bar[st], (uint32_t)((k / kStages) & 1));
+        const int nch = min(kTileChunks, nchunks - k * kTileChunks);
+        const float4* __restrict__ tile = tiles + st * (kTileBytes / 16);
+        for (int c = 0; c < nch; ++c) {
+            const float4* __restrict__ cg = tile + c * (kGroupsPerChunk * 3);
+#pragma unroll
+            for (int g = 0; g < kGroupsPerChunk; ++g) {
+                const float4 X = cg[3 * g], Y = cg[3 * g + 1], Z = cg[3 * g + 2];
+                const u64 X01 = pack2(X.x, X.y), X23 = pack2(X.z, X.w);
+                const u64 Y01 = pack2(Y.x, Y.y), Y23 = pack2(Y.z, Y.w);
+                const u64 Z01 = pack2(Z.x, Z.y), Z23 = pack2(Z.z, Z.w);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float a0, a1, a2, a3;
+                    unpack2(sqdist_pair(QX[r], QY[r], QZ[r], X01, Y01, Z01), a0, a1);
+                    unpack2(sqdist_pair(QX[r], QY[r], QZ[r], X23, Y23, Z23), a2, a3);
+                    best[r] = min3(best[r], a0, a1);
+                    best[r] = min3(best[r], a2, a3);
+                }
+            }
+            const unsigned gid = (unsigned)(chunk0 + k * kTileChunks + c);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (best[r] < prev[r]) bch[r] = gid;
+                prev[r] = best[r];
+            }
+        }
+        __syncthreads();                                   // everyone is done with stage st
+        if (tid == 0 && k + kStages < ntiles) issue(k + kStages);
+    }
+
+    u64* __restrict__ keys = D.keys + (int64_t)b * D.nq;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = qbase + r * THREADS + tid;
+        if (i < D.nq) {
+            const u64 key = ((u64)__float_as_uint(best[r]) << 32) | (u64)bch[r];
+            if (D.splits == 1) keys[i] = key;
+            else atomicMin(&keys[i], key);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- finalize
+// One thread per query: decode (dist, chunk) and re-scan that chunk for the first target whose
+// distance equals the minimum (same arithmetic as the main loop => guaranteed hit).
+__device__ __forceinline__ int rescan_chunk(const float* __restrict__ tpacked_b, unsigned chunk, int chunk_pts,
+                                            int nt_pad, float qx, float qy, float qz, float dmin) {
+    const int start = (int)chunk * chunk_pts;
+    const int end = min(start + chunk_pts, nt_pad);
+    const float4* __restrict__ cg = reinterpret_cast<const float4*>(tpacked_b) + (start / 4) * 3;
+    const int ngroups = (end - start) / 4;
+    for (int g = 0; g < ngroups; ++g) {
+        const float4 X = __ldg(cg + 3 * g), Y = __ldg(cg + 3 * g + 1), Z = __ldg(cg + 3 * g + 2);
+        if (sqdist_scalar(qx, qy, qz, X.x, Y.x, Z.x) == dmin) return start + 4 * g;
+        if (sqdist_scalar(qx, qy, qz, X.y, Y.y, Z.y) == dmin) return start + 4 * g + 1;
+        if (sqdist_scalar(qx, qy, qz, X.z, Y.z, Z.z) == dmin) return start + 4 * g + 2;
+        if (sqdist_scalar(qx, qy, qz, X.w, Y.w, Z.w) == dmin) return start + 4 * g + 3;
+    }
+    return start;   // unreachable for finite inputs (the minimum was produced by this very arithmetic)
+}
+
+__global__ void knn1_finalize_kernel(const KnnParams p, int dir_only) {
+    for (int dir = 0; dir < p.ndir; ++dir) {
+        if (dir_only >= 0 && dir != dir_only) continue;
+        const KnnDir& D = p.dir[dir];
+        const int64_t total = (int64_t)p.B * D.nq;
+        for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+             e += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t b = e / D.nq;
+            const int64_t i = e - b * D.nq;
+            const u64 key = D.keys[e];
+            const float dmin = __uint_as_float((unsigned)(key >> 32));
+            const unsigned chunk = (unsigned)(key & 0xffffffffu);
+            const float* qp = D.q + e * 3;
+            int j = rescan_chunk(D.tpacked + b * (int64_t)D.nt_pad * 3, chunk, D.chunk_pts, D.nt_pad, qp[0], qp[1], qp[2], dmin);
+            if (j >= D.nt) j = 0;
+            if (D.out_dists) D.out_dists[e] = dmin;
+            if (D.out_idx) D.out_idx[e] = (int64_t)j;
+            (void)i;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- host side
+static int choose_splits(int64_t B, int qblocks, int chunks_total, int ndir) {
+    // Aim for >= ~8 CTAs per SM-slot so the hardware scheduler balances the tail, but keep
+    // at least 2 tiles (1024 targets) per item so prologue/epilogue stay amortised.
+    const int64_t want = 148 * 2 * 6;
+    const int64_t base = B * qblocks * ndir;
+    int s = (int)ceil_div(want, base > 0 ? base : 1);
+    const int max_s = std::max(1, chunks_total / (2 * kTileChunks));
+    s = std::max(1, std::min(s, max_s));
+    return s;
+}
+
+template <int R, int THREADS>
+static int launch_main(KnnParams& p, cudaStream_t stream) {
+    const int QB = R * THREADS;
+    int64_t items = 0;
+    for (int d = 0; d < p.ndir; ++d) {
+        KnnDir& D = p.dir[d];
+        D.qblocks = (int)ceil_div(D.nq, QB);
+        D.splits = choose_splits(p.B, D.qblocks, D.nt_pad / kChunk, p.ndir);
+        const int64_t it = (int64_t)p.B * D.qblocks * D.splits;
+        if (d == 0) p.items0 = (int)it;
+        items += it;
+    }
+    if (items <= 0) return kOk;
+    if (items > 0x7fffffff) return kErrUnsupported;
+    // keys must start at +max when partial results are merged with atomicMin
+    for (int d = 0; d < p.ndir; ++d) {
+        KnnDir& D = p.dir[d];
+        if (D.splits > 1 && !D.keys_preset) {
+            if (cudaMemsetAsync(D.keys, 0xff, sizeof(u64) * (size_t)p.B * D.nq, stream) != cudaSuccess) return kErrLaunch;
+        }
+    }
+    const size_t smem = (size_t)kStages * kTileBytes;
+    knn1_main_kernel<R, THREADS><<<(unsigned)items, THREADS, smem, stream>>>(p);
+    REART_CHECK_LAUNCH();
+    return kOk;
+}
+
+int launch_knn1_search(KnnParams& p, cudaStream_t stream) {
+    // Small query sets: fewer queries per CTA so tiny problems (B=400, N=20) do not idle lanes.
+    int64_t maxq = 0;
+    for (int d = 0; d < p.ndir; ++d) maxq = std::max<int64_t>(maxq, p.dir[d].nq);
+    if (maxq <= 512) return launch_main<4, 128>(p, stream);
+    return launch_main<8, 256>(p, stream);
+}
+
+int launch_knn1_finalize(const KnnParams& p, cudaStream_t stream) {
+    int64_t total = 0;
+    for (int d = 0; d < p.ndir; ++d) total = std::max<int64_t>(total, (int64_t)p.B * p.dir[d].nq);
+    if (total <= 0) return kOk;
+    const int threads = 256;
+    const int blocks = (int)(int64_t)std::min<int64_t>(ceil_div(total, threads), 148 * 16);
+    knn1_finalize_kernel<<<blocks, threads, 0, stream>>>(p, -1);
+    REART_CHECK_LAUNCH();
+    return kOk;
+}
+
+}  // namespace reart
