@@ -74,6 +74,112 @@ REART_API int reart_chamfer_bidir_bwd(const float* src, const float* tgt, const 
                             float* grad_tgt, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Packed cloud layout used by the searches: groups of 4 points [x0..x3|y0..y3|z0..z3], +INF padded to a
+ * multiple of 32 points per batch element.  Observed frames are constant over an optimisation, so callers
+ * pack them once (reart_pack_cloud) and reuse the buffer every iteration.
+ * ------------------------------------------------------------------------------------------- */
+REART_API int64_t reart_packed_bytes(int64_t B, int64_t P);
+REART_API int reart_pack_cloud(const float* pts, int64_t B, int64_t P, float* packed, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Soft-assignment skinning.
+ * Replaces the bmm + broadcast-multiply + sum of networks/model.py:63-69 (BaseModel.forward),
+ * networks/model.py:161-165 (KinematicModel.forward) and utils/model_utils.py:54-67 (compute_pc_transform):
+ *   out[t,n,:] = sum_p W[n,p] * (R[t,p] @ cano[n] + tr[t,p])
+ * cano [N,3], W [N,P] float32, R [T,P,3,3], tr [T,P,3] -> out [T,N,3].
+ * Backward: g [T,N,3] -> gW [N,P], gR [T,P,3,3], gtr [T,P,3] (all overwritten).
+ * ------------------------------------------------------------------------------------------- */
+REART_API int reart_skin_fwd(const float* cano, const float* W, const float* R, const float* tr, int64_t T, int64_t N,
+                             int64_t P, float* out, void* stream);
+REART_API int reart_skin_bwd(const float* cano, const float* W, const float* R, const float* tr, const float* g,
+                             int64_t T, int64_t N, int64_t P, float* gW, float* gR, float* gtr, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The whole per-iteration energy, fused: skin -> bidirectional Chamfer -> sum -> backward to the
+ * skinning inputs.  Equivalent to (networks/model.py:63-69) -> recon_loss (networks/loss.py:24-29,
+ * i.e. ChamferDistance(bidirectional=True) utils/chamfer.py:78-123 + torch.sum) -> autograd backward.
+ *   cano [N,3], W [N,P], R [T,P,3,3], tr [T,P,3]; tgt [T,M,3] observed frames and their packed copy.
+ * Outputs: skinned [T,N,3]; loss[1] (double, sum of all per-point squared distances, both directions);
+ *          gW [N,P], gR [T,P,3,3], gtr [T,P,3]; g_skinned [T,N,3] (dLoss/dskinned, may be NULL).
+ * compute_grad == 0 stops after the loss.
+ * ------------------------------------------------------------------------------------------- */
+REART_API int64_t reart_energy_workspace_bytes(int64_t T, int64_t N, int64_t M);
+REART_API int reart_skinned_chamfer_fwd_bwd(const float* cano, const float* W, const float* R, const float* tr,
+                                            const float* tgt, const float* tgt_packed, int64_t T, int64_t N, int64_t M,
+                                            int64_t P, float* skinned, double* loss, float* gW, float* gR, float* gtr,
+                                            float* g_skinned, int compute_grad, void* workspace,
+                                            int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * 6D rotation representation -> matrix (Gram-Schmidt).
+ * Replaces screw_se3/geo_utils.py:632-651 (rotation_6d_to_matrix); d6 [B,6] -> R [B,3,3].
+ * Backward: gR [B,3,3] -> gd6 [B,6].
+ * ------------------------------------------------------------------------------------------- */
+REART_API int reart_rot6d_fwd(const float* d6, int64_t B, float* R, void* stream);
+REART_API int reart_rot6d_bwd(const float* d6, const float* gR, int64_t B, float* gd6, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Screw parameters -> 4x4 transform.
+ * Replaces transform_from_exponential_coordinates(screw_param_to_exponential_coordinates(l, m, theta, d))
+ * (screw_se3/screw_utils.py:6-30 over se3_exp_map, screw_se3/geo_utils.py:147-222), quirks included.
+ *   l,m [B,3], theta,d [B] -> M [B,4,4].   Backward: gM [B,4,4] -> gl, gm [B,3], gtheta, gd [B].
+ * ------------------------------------------------------------------------------------------- */
+REART_API int reart_screw_to_transform_fwd(const float* l, const float* m, const float* theta, const float* d,
+                                           int64_t B, float* M, void* stream);
+REART_API int reart_screw_to_transform_bwd(const float* l, const float* m, const float* theta, const float* d,
+                                           const float* gM, int64_t B, float* gl, float* gm, float* gtheta, float* gd,
+                                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Forward kinematics over the joint tree.
+ * Replaces fk(paths_to_base, reverse_topo, edge_index, axis_list, moment_list, theta_list,
+ *             distance_list, joint_type_list)  (utils/kinematic_utils.py:151-198).
+ * The dict-based tree is passed flattened (device int32 arrays): order[P] = reverse_topo (root first),
+ * parent[P] (-1 for the root), edge[P] = index of the edge joining a part to its parent,
+ * joint_type[E] (0 as given / 1 revolute / 2 prismatic) or NULL; distance [T,E] or NULL (d = 1e-6).
+ *   axis, moment [E,3], theta [T,E] -> out [T,P,4,4] indexed by part id.
+ * Backward: g_out [T,P,4,4] -> g_axis, g_moment [E,3], g_theta [T,E], g_dist [T,E] (NULL if distance NULL);
+ * workspace: T*P*16 floats.
+ * ------------------------------------------------------------------------------------------- */
+REART_API int reart_fk_fwd(const float* axis, const float* moment, const float* theta, const float* distance,
+                           const int32_t* order, const int32_t* parent, const int32_t* edge, const int32_t* joint_type,
+                           int64_t T, int64_t P, float* out, void* stream);
+REART_API int reart_fk_bwd(const float* axis, const float* moment, const float* theta, const float* distance,
+                           const int32_t* order, const int32_t* parent, const int32_t* edge, const int32_t* joint_type,
+                           int64_t T, int64_t P, const float* fk_out, const float* g_out, float* g_axis,
+                           float* g_moment, float* g_theta, float* g_dist, float* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Small-k nearest neighbours with EUCLIDEAN distances, ascending, ties -> lowest index.
+ * Replaces knn_cuda.KNN(k, transpose_mode=True)(ref, query) (KNN_CUDA 0.2; call sites
+ * utils/flow_utils.py:158, utils/model_utils.py:42):  ref [B,n,3], query [B,m,3] -> dist, idx [B,m,k], k <= 8.
+ * ------------------------------------------------------------------------------------------- */
+REART_API int reart_knn(const float* ref, const float* query, int64_t B, int64_t n, int64_t m, int k, float* dist,
+                        int64_t* idx, void* stream);
+
+/* Flow blending for all frame pairs at once.  Replaces the Python loop over
+ * blend_anchor_motion(query, ref, flow, knn_flow, return_mask=True) (utils/flow_utils.py:147-170,
+ * called T times per iteration from run_robot.py:199-202) with k = 3.
+ *   query [T,m,3]; ref_cat/flow_cat [sum n_t,3] (the per-pair lists concatenated);
+ *   ref_offsets [T+1] int64 DEVICE array of row offsets -> blended [T,m,3], mask [T,m] (uint8 0/1). */
+REART_API int reart_knn3_blend(const float* query, const float* ref_cat, const float* flow_cat,
+                               const int64_t* ref_offsets, int64_t T, int64_t m, float* blended, uint8_t* mask,
+                               void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Furthest point sampling / ball query (the two reachable kernels of the reference's PointNet++ extension).
+ * Replace pointnet2_cuda.furthest_point_sampling_wrapper(B, N, npoint, xyz, temp, out) and
+ * pointnet2_cuda.ball_query_wrapper(B, N, npoint, radius, nsample, new_xyz, xyz, idx)
+ * (networks/pointnet_lib/pointnet2_utils.py:29,263; kernels networks/pointnet_lib/src/sampling_gpu.cu:93-209,
+ * ball_query_gpu.cu:9-45).  FPS starts at index 0; arg-max ties -> lowest index.  N <= 32768 per cloud.
+ *   xyz [B,N,3] -> out [B,npoint] int32;   new_xyz [B,m,3], xyz [B,N,3] -> idx [B,m,nsample] int32
+ *   (idx must be zero-filled by the caller, as the reference does).
+ * ------------------------------------------------------------------------------------------- */
+REART_API int reart_fps(const float* xyz, int64_t B, int64_t N, int64_t npoint, int32_t* out, void* stream);
+REART_API int reart_ball_query(const float* new_xyz, const float* xyz, int64_t B, int64_t N, int64_t m, float radius,
+                               int nsample, int32_t* idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * FP32-pipe micro-benchmark (roofline denominator).  Runs variant
  * 0..5 (see csrc/probe.cu) once warm and once timed with CUDA events on `stream`, SYNCHRONISES,
  * and returns milliseconds and the number of measured lane-operations per thread.

@@ -27,6 +27,24 @@ SIGNATURES = {
     "reart_chamfer_bidir_fwd": (_c_int, [_vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp, _vp, _vp, _c_i64, _vp]),
     "reart_knn1_bwd": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp]),
     "reart_chamfer_bidir_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp]),
+    "reart_packed_bytes": (_c_i64, [_c_i64, _c_i64]),
+    "reart_pack_cloud": (_c_int, [_vp, _c_i64, _c_i64, _vp, _vp]),
+    "reart_skin_fwd": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp]),
+    "reart_skin_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp, _vp]),
+    "reart_energy_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i64]),
+    "reart_skinned_chamfer_fwd_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _c_i64, _vp, _vp,
+                                               _vp, _vp, _vp, _vp, _c_int, _vp, _c_i64, _vp]),
+    "reart_rot6d_fwd": (_c_int, [_vp, _c_i64, _vp, _vp]),
+    "reart_rot6d_bwd": (_c_int, [_vp, _vp, _c_i64, _vp, _vp]),
+    "reart_screw_to_transform_fwd": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _vp, _vp]),
+    "reart_screw_to_transform_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _vp, _vp, _vp, _vp, _vp]),
+    "reart_fk_fwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _vp, _vp]),
+    "reart_fk_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                              _vp, _vp]),
+    "reart_knn": (_c_int, [_vp, _vp, _c_i64, _c_i64, _c_i64, _c_int, _vp, _vp, _vp]),
+    "reart_knn3_blend": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_i64, _vp, _vp, _vp]),
+    "reart_fps": (_c_int, [_vp, _c_i64, _c_i64, _c_i64, _vp, _vp]),
+    "reart_ball_query": (_c_int, [_vp, _vp, _c_i64, _c_i64, _c_i64, ctypes.c_float, _c_int, _vp, _vp]),
     "reart_fp32_probe": (_c_int, [_c_int, _c_int, _c_int, _vp, _vp, ctypes.POINTER(ctypes.c_double),
                                   ctypes.POINTER(ctypes.c_double), _vp]),
 }

@@ -144,6 +144,159 @@ int reart_chamfer_bidir_bwd(const float* src, const float* tgt, const int64_t* i
     return launch_chamfer_bidir_bwd(src, tgt, i_fwd, i_bwd, g_fwd, g_bwd, B, N, M, grad_src, grad_tgt, stream);
 }
 
+int64_t reart_packed_bytes(int64_t B, int64_t P) {
+    if (B < 0 || P < 0) return -1;
+    return packed_bytes(B, P);
+}
+
+int reart_pack_cloud(const float* pts, int64_t B, int64_t P, float* packed, void* stream_) {
+    if (B < 0 || P < 0 || !fits_int(padded_points(P))) return REART_ERR_INVALID_ARG;
+    if (B == 0) return REART_OK;
+    if (!packed || (P > 0 && !pts)) return REART_ERR_INVALID_ARG;
+    return launch_pack_cloud(pts, packed, B, P, static_cast<cudaStream_t>(stream_));
+}
+
+int reart_skin_fwd(const float* cano, const float* W, const float* R, const float* tr, int64_t T, int64_t N, int64_t P,
+                   float* out, void* stream_) {
+    if (T < 0 || N < 0 || P < 0 || !fits_int(T) || !fits_int(N)) return REART_ERR_INVALID_ARG;
+    if (T == 0 || N == 0) return REART_OK;
+    if (!cano || !W || !R || !tr || !out) return REART_ERR_INVALID_ARG;
+    return launch_skin_fwd(cano, W, R, tr, T, N, P, out, nullptr, static_cast<cudaStream_t>(stream_));
+}
+
+int reart_skin_bwd(const float* cano, const float* W, const float* R, const float* tr, const float* g, int64_t T,
+                   int64_t N, int64_t P, float* gW, float* gR, float* gtr, void* stream_) {
+    if (T < 0 || N < 0 || P < 0 || !fits_int(T) || !fits_int(N)) return REART_ERR_INVALID_ARG;
+    if ((N * P > 0 && !gW) || (T * P > 0 && (!gR || !gtr))) return REART_ERR_INVALID_ARG;
+    if (T > 0 && N > 0 && (!cano || !W || !R || !tr || !g)) return REART_ERR_INVALID_ARG;
+    return launch_skin_bwd(cano, W, R, tr, g, T, N, P, gW, gR, gtr, static_cast<cudaStream_t>(stream_));
+}
+
+int64_t reart_energy_workspace_bytes(int64_t T, int64_t N, int64_t M) {
+    if (T < 0 || N < 0 || M < 0) return -1;
+    return packed_bytes(T, N) + keys_bytes(T, N) + keys_bytes(T, M) + align_up(T * N * 12) + kAlign;
+}
+
+int reart_skinned_chamfer_fwd_bwd(const float* cano, const float* W, const float* R, const float* tr, const float* tgt,
+                                  const float* tgt_packed, int64_t T, int64_t N, int64_t M, int64_t P, float* skinned,
+                                  double* loss, float* gW, float* gR, float* gtr, float* g_skinned, int compute_grad,
+                                  void* workspace, int64_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (T <= 0 || N <= 0 || M <= 0 || P <= 0 || !fits_int(T) || !fits_int(padded_points(N)) || !fits_int(padded_points(M)))
+        return REART_ERR_INVALID_ARG;
+    if (!cano || !W || !R || !tr || !tgt || !tgt_packed || !skinned || !loss) return REART_ERR_INVALID_ARG;
+    if (compute_grad && (!gW || !gR || !gtr)) return REART_ERR_INVALID_ARG;
+    Carver ws(workspace, workspace_bytes);
+    float* psrc = ws.take<float>(T * packed_floats_per_batch(N));
+    u64* ka = ws.take<u64>(T * N);
+    u64* kb = ws.take<u64>(T * M);
+    float* gs = g_skinned ? g_skinned : ws.take<float>(T * N * 3);
+    if (!ws.ok) return REART_ERR_WORKSPACE;
+    int rc = launch_skin_fwd(cano, W, R, tr, T, N, P, skinned, psrc, stream);
+    if (rc) return rc;
+    SymParams sp = {};
+    sp.a = skinned; sp.b_packed = tgt_packed; sp.keys_a = ka; sp.keys_b = kb;
+    sp.B = (int)T; sp.na = (int)N; sp.nb = (int)M; sp.nb_pad = (int)padded_points(M);
+    rc = launch_chamfer_sym(sp, stream);
+    if (rc) return rc;
+    if (cudaMemsetAsync(loss, 0, sizeof(double), stream) != cudaSuccess) return REART_ERR_LAUNCH;
+    if (cudaMemsetAsync(gs, 0, sizeof(float) * (size_t)(T * N * 3), stream) != cudaSuccess) return REART_ERR_LAUNCH;
+    EnergyParams ep = {};
+    ep.src = skinned; ep.tgt = tgt; ep.src_packed = psrc; ep.tgt_packed = tgt_packed; ep.keys_a = ka; ep.keys_b = kb;
+    ep.B = (int)T; ep.N = (int)N; ep.M = (int)M; ep.n_pad = (int)padded_points(N); ep.m_pad = (int)padded_points(M);
+    ep.row_chunk_pts = kChunk; ep.col_chunk_pts = sp.col_chunk_pts; ep.gscale = 1.0f; ep.g_src = gs; ep.loss = loss;
+    rc = launch_energy_bwd(ep, stream);
+    if (rc || !compute_grad) return rc;
+    return launch_skin_bwd(cano, W, R, tr, gs, T, N, P, gW, gR, gtr, stream);
+}
+
+int reart_rot6d_fwd(const float* d6, int64_t B, float* R, void* stream_) {
+    if (B < 0) return REART_ERR_INVALID_ARG;
+    if (B == 0) return REART_OK;
+    if (!d6 || !R) return REART_ERR_INVALID_ARG;
+    return launch_rot6d_fwd(d6, B, R, static_cast<cudaStream_t>(stream_));
+}
+
+int reart_rot6d_bwd(const float* d6, const float* gR, int64_t B, float* gd6, void* stream_) {
+    if (B < 0) return REART_ERR_INVALID_ARG;
+    if (B == 0) return REART_OK;
+    if (!d6 || !gR || !gd6) return REART_ERR_INVALID_ARG;
+    return launch_rot6d_bwd(d6, gR, B, gd6, static_cast<cudaStream_t>(stream_));
+}
+
+int reart_screw_to_transform_fwd(const float* l, const float* m, const float* theta, const float* d, int64_t B,
+                                 float* M, void* stream_) {
+    if (B < 0) return REART_ERR_INVALID_ARG;
+    if (B == 0) return REART_OK;
+    if (!l || !m || !theta || !d || !M) return REART_ERR_INVALID_ARG;
+    return launch_screw_fwd(l, m, theta, d, B, M, static_cast<cudaStream_t>(stream_));
+}
+
+int reart_screw_to_transform_bwd(const float* l, const float* m, const float* theta, const float* d, const float* gM,
+                                 int64_t B, float* gl, float* gm, float* gtheta, float* gd, void* stream_) {
+    if (B < 0) return REART_ERR_INVALID_ARG;
+    if (B == 0) return REART_OK;
+    if (!l || !m || !theta || !d || !gM || !gl || !gm || !gtheta || !gd) return REART_ERR_INVALID_ARG;
+    return launch_screw_bwd(l, m, theta, d, gM, B, gl, gm, gtheta, gd, static_cast<cudaStream_t>(stream_));
+}
+
+int reart_fk_fwd(const float* axis, const float* moment, const float* theta, const float* distance,
+                 const int32_t* order, const int32_t* parent, const int32_t* edge, const int32_t* joint_type, int64_t T,
+                 int64_t P, float* out, void* stream_) {
+    if (T < 0 || P < 0 || !fits_int(T) || !fits_int(P)) return REART_ERR_INVALID_ARG;
+    if (T == 0 || P == 0) return REART_OK;
+    if (!order || !parent || !edge || !out || (P > 1 && (!axis || !moment || !theta))) return REART_ERR_INVALID_ARG;
+    FkParams p = {axis, moment, theta, distance, order, parent, edge, joint_type, (int)T, (int)P};
+    return launch_fk_fwd(p, out, static_cast<cudaStream_t>(stream_));
+}
+
+int reart_fk_bwd(const float* axis, const float* moment, const float* theta, const float* distance,
+                 const int32_t* order, const int32_t* parent, const int32_t* edge, const int32_t* joint_type, int64_t T,
+                 int64_t P, const float* fk_out, const float* g_out, float* g_axis, float* g_moment, float* g_theta,
+                 float* g_dist, float* workspace, void* stream_) {
+    if (T < 0 || P < 0 || !fits_int(T) || !fits_int(P)) return REART_ERR_INVALID_ARG;
+    if (T == 0 || P <= 1) return REART_OK;
+    if (!order || !parent || !edge || !fk_out || !g_out || !axis || !moment || !theta || !g_axis || !g_moment ||
+        !g_theta || !workspace)
+        return REART_ERR_INVALID_ARG;
+    FkParams p = {axis, moment, theta, distance, order, parent, edge, joint_type, (int)T, (int)P};
+    return launch_fk_bwd(p, fk_out, g_out, workspace, g_axis, g_moment, g_theta, distance ? g_dist : nullptr,
+                         static_cast<cudaStream_t>(stream_));
+}
+
+int reart_knn(const float* ref, const float* query, int64_t B, int64_t n, int64_t m, int k, float* dist, int64_t* idx,
+              void* stream_) {
+    if (B < 0 || n < 0 || m < 0 || k < 1 || k > 8 || !fits_int(n) || !fits_int(m)) return REART_ERR_INVALID_ARG;
+    if (B == 0 || m == 0) return REART_OK;
+    if (n < k) return REART_ERR_INVALID_ARG;
+    if (!ref || !query || !dist || !idx) return REART_ERR_INVALID_ARG;
+    return launch_knn(ref, query, B, n, m, k, dist, idx, static_cast<cudaStream_t>(stream_));
+}
+
+int reart_knn3_blend(const float* query, const float* ref_cat, const float* flow_cat, const int64_t* ref_offsets,
+                     int64_t T, int64_t m, float* blended, uint8_t* mask, void* stream_) {
+    if (T < 0 || m < 0 || !fits_int(m)) return REART_ERR_INVALID_ARG;
+    if (T == 0 || m == 0) return REART_OK;
+    if (!query || !ref_cat || !flow_cat || !ref_offsets || !blended) return REART_ERR_INVALID_ARG;
+    return launch_knn3_blend(query, ref_cat, flow_cat, ref_offsets, T, m, blended, mask,
+                             static_cast<cudaStream_t>(stream_));
+}
+
+int reart_fps(const float* xyz, int64_t B, int64_t N, int64_t npoint, int32_t* out, void* stream_) {
+    if (B < 0 || N < 0 || npoint < 0) return REART_ERR_INVALID_ARG;
+    if (B == 0 || npoint == 0) return REART_OK;
+    if (!xyz || !out || N == 0) return REART_ERR_INVALID_ARG;
+    return launch_fps(xyz, B, N, npoint, out, static_cast<cudaStream_t>(stream_));
+}
+
+int reart_ball_query(const float* new_xyz, const float* xyz, int64_t B, int64_t N, int64_t m, float radius,
+                     int nsample, int32_t* idx, void* stream_) {
+    if (B < 0 || N < 0 || m < 0 || nsample < 0 || !fits_int(N) || !fits_int(m)) return REART_ERR_INVALID_ARG;
+    if (B == 0 || m == 0 || nsample == 0) return REART_OK;
+    if (!new_xyz || !idx || (N > 0 && !xyz)) return REART_ERR_INVALID_ARG;
+    return launch_ball_query(new_xyz, xyz, B, N, m, radius, nsample, idx, static_cast<cudaStream_t>(stream_));
+}
+
 int reart_fp32_probe(int variant, int iters, int blocks, const float* scratch_in, float* scratch_out, double* ms,
                      double* ops_per_thread, void* stream_) {
     return launch_probe(variant, iters, blocks, scratch_in, scratch_out, ms, ops_per_thread,

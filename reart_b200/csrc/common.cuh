@@ -114,4 +114,23 @@ constexpr int kGroupFloats = 12;         // floats per group of 4 points
 __host__ __device__ __forceinline__ int64_t padded_points(int64_t P) { return round_up(P > 0 ? P : 1, kChunk); }
 __host__ __device__ __forceinline__ int64_t packed_floats_per_batch(int64_t P) { return padded_points(P) * 3; }
 
+// Re-scan one arg-min chunk of a packed cloud for the FIRST point whose distance to q equals dmin
+// (same arithmetic as the search loops => guaranteed hit for finite inputs).  Used by the finalize /
+// fused-backward kernels to turn (min, chunk) keys into exact lowest-index arg-mins.
+__device__ __forceinline__ int rescan_chunk(const float* __restrict__ tpacked_b, unsigned chunk, int chunk_pts,
+                                            int nt_pad, float qx, float qy, float qz, float dmin) {
+    const int start = (int)chunk * chunk_pts;
+    const int end = min(start + chunk_pts, nt_pad);
+    const float4* __restrict__ cg = reinterpret_cast<const float4*>(tpacked_b) + (start / 4) * 3;
+    const int ngroups = (end - start) / 4;
+    for (int g = 0; g < ngroups; ++g) {
+        const float4 X = __ldg(cg + 3 * g), Y = __ldg(cg + 3 * g + 1), Z = __ldg(cg + 3 * g + 2);
+        if (sqdist_scalar(qx, qy, qz, X.x, Y.x, Z.x) == dmin) return start + 4 * g;
+        if (sqdist_scalar(qx, qy, qz, X.y, Y.y, Z.y) == dmin) return start + 4 * g + 1;
+        if (sqdist_scalar(qx, qy, qz, X.z, Y.z, Z.z) == dmin) return start + 4 * g + 2;
+        if (sqdist_scalar(qx, qy, qz, X.w, Y.w, Z.w) == dmin) return start + 4 * g + 3;
+    }
+    return start;   // unreachable for finite inputs (the minimum was produced by this very arithmetic)
+}
+
 }  // namespace reart

@@ -52,6 +52,61 @@ int launch_chamfer_bidir_bwd(const float* src, const float* tgt, const int64_t* 
                              const float* g_fwd, const float* g_bwd, int64_t B, int64_t N, int64_t M, float* grad_src,
                              float* grad_tgt, cudaStream_t stream);
 
+int launch_skin_fwd(const float* cano, const float* W, const float* R, const float* tr, int64_t T, int64_t N, int64_t P,
+                    float* out, float* out_packed, cudaStream_t stream);
+int launch_skin_bwd(const float* cano, const float* W, const float* R, const float* tr, const float* g, int64_t T,
+                    int64_t N, int64_t P, float* gW, float* gR, float* gtr, cudaStream_t stream);
+
+int launch_rot6d_fwd(const float* d6, int64_t B, float* R, cudaStream_t stream);
+int launch_rot6d_bwd(const float* d6, const float* gR, int64_t B, float* gd6, cudaStream_t stream);
+int launch_screw_fwd(const float* l, const float* m, const float* theta, const float* d, int64_t B, float* M,
+                     cudaStream_t stream);
+int launch_screw_bwd(const float* l, const float* m, const float* theta, const float* d, const float* gM, int64_t B,
+                     float* gl, float* gm, float* gtheta, float* gd, cudaStream_t stream);
+
+// Flattened joint tree for forward kinematics (utils/kinematic_utils.py:151-198).
+struct FkParams {
+    const float* axis;            // [E,3]
+    const float* moment;          // [E,3]
+    const float* theta;           // [T,E]
+    const float* distance;        // [T,E] or null (=> d = 1e-6)
+    const int32_t* order;         // [P] parts root-first (reverse_topo)
+    const int32_t* parent;        // [P] parent part id, -1 for the root
+    const int32_t* edge;          // [P] edge index joining part to its parent
+    const int32_t* joint_type;    // [E] 0 as given, 1 revolute, 2 prismatic; or null
+    int T, P;
+};
+int launch_fk_fwd(const FkParams& p, float* out, cudaStream_t stream);
+int launch_fk_bwd(const FkParams& p, const float* fk, const float* g_out, float* gwork, float* g_axis, float* g_moment,
+                  float* g_theta, float* g_dist, cudaStream_t stream);
+
+// Fused loss + gradient of the bidirectional Chamfer energy from the search keys (energy.cu).
+struct EnergyParams {
+    const float* src;             // [B,N,3] skinned cloud
+    const float* tgt;             // [B,M,3] observed frames
+    const float* src_packed;      // packed copies (re-scan)
+    const float* tgt_packed;
+    const unsigned long long* keys_a;   // [B,N] row keys
+    const unsigned long long* keys_b;   // [B,M] column keys
+    int B, N, M, n_pad, m_pad;
+    int row_chunk_pts, col_chunk_pts;
+    float gscale;                 // upstream gradient of every per-point distance (1 for torch.sum)
+    float* g_src;                 // [B,N,3], zero on entry
+    double* loss;                 // [1], zero on entry: sum of all per-point distances
+    float* d_fwd; int64_t* i_fwd; // optional [B,N]
+    float* d_bwd; int64_t* i_bwd; // optional [B,M]
+};
+int launch_energy_bwd(const EnergyParams& p, cudaStream_t stream);
+
+int launch_knn(const float* ref, const float* query, int64_t B, int64_t n, int64_t m, int k, float* dist, int64_t* idx,
+               cudaStream_t stream);
+int launch_knn3_blend(const float* query, const float* ref_cat, const float* flow_cat, const int64_t* ref_off,
+                      int64_t T, int64_t m, float* blended, unsigned char* mask, cudaStream_t stream);
+
+int launch_fps(const float* xyz, int64_t B, int64_t N, int64_t m, int* out, cudaStream_t stream);
+int launch_ball_query(const float* new_xyz, const float* xyz, int64_t B, int64_t N, int64_t m, float radius,
+                      int nsample, int* idx, cudaStream_t stream);
+
 int launch_probe(int variant, int iters, int blocks, const float* in, float* out, double* ms, double* ops_per_thread,
                  cudaStream_t stream);
 

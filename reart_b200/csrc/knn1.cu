@@ -170,22 +170,6 @@ __global__ void __launch_bounds__(THREADS, (R <= 8 && THREADS <= 256) ? 2 : 1) k
 // ----------------------------------------------------------------------------- finalize
 // One thread per query: decode (dist, chunk) and re-scan that chunk for the first target whose
 // distance equals the minimum (same arithmetic as the main loop => guaranteed hit).
-__device__ __forceinline__ int rescan_chunk(const float* __restrict__ tpacked_b, unsigned chunk, int chunk_pts,
-                                            int nt_pad, float qx, float qy, float qz, float dmin) {
-    const int start = (int)chunk * chunk_pts;
-    const int end = min(start + chunk_pts, nt_pad);
-    const float4* __restrict__ cg = reinterpret_cast<const float4*>(tpacked_b) + (start / 4) * 3;
-    const int ngroups = (end - start) / 4;
-    for (int g = 0; g < ngroups; ++g) {
-        const float4 X = __ldg(cg + 3 * g), Y = __ldg(cg + 3 * g + 1), Z = __ldg(cg + 3 * g + 2);
-        if (sqdist_scalar(qx, qy, qz, X.x, Y.x, Z.x) == dmin) return start + 4 * g;
-        if (sqdist_scalar(qx, qy, qz, X.y, Y.y, Z.y) == dmin) return start + 4 * g + 1;
-        if (sqdist_scalar(qx, qy, qz, X.z, Y.z, Z.z) == dmin) return start + 4 * g + 2;
-        if (sqdist_scalar(qx, qy, qz, X.w, Y.w, Z.w) == dmin) return start + 4 * g + 3;
-    }
-    return start;   // unreachable for finite inputs (the minimum was produced by this very arithmetic)
-}
-
 __global__ void knn1_finalize_kernel(const KnnParams p, int dir_only) {
     for (int dir = 0; dir < p.ndir; ++dir) {
         if (dir_only >= 0 && dir != dir_only) continue;

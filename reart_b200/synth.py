@@ -1,0 +1,67 @@
+"""Deterministic synthetic sequences of the shapes named in BASELINE.json.
+
+An articulated object = P boxes on a random joint tree, surface-sampled to N canonical points in roughly
+[-0.35, 0.35]^3 (the nao range); every frame poses the parts by composing per-joint rotations about the
+joint anchors (theta ~ U(-1,1) rad) and re-samples M observed points with N(0, 1e-3) noise.  numpy only,
+seed 2 by default (the reference's --manual_seed default, run_robot.py:364).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _rodrigues(axis, angle):
+    axis = axis / np.linalg.norm(axis)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    return np.eye(3) + np.sin(angle) * K + (1 - np.cos(angle)) * (K @ K)
+
+
+def make_sequence(T: int, N: int, P: int, seed: int = 2, M: int | None = None, noise: float = 1e-3):
+    """Returns dict(cano [N,3] f32, part [N] i64, frames [T,M,3] f32, pose [T,P,4,4] f32 GT part poses,
+    parent [P], anchors [P,3], axes [P,3])."""
+    M = N if M is None else M
+    rng = np.random.default_rng(seed)
+    parent = np.full(P, -1, np.int64)
+    centers = np.zeros((P, 3))
+    half = np.zeros((P, 3))
+    anchors = np.zeros((P, 3))
+    axes = rng.standard_normal((P, 3))
+    half[0] = rng.uniform(0.04, 0.09, 3)
+    for p in range(1, P):
+        par = int(rng.integers(0, p))
+        parent[p] = par
+        half[p] = rng.uniform(0.02, 0.07, 3)
+        direction = rng.standard_normal(3)
+        direction /= np.linalg.norm(direction)
+        anchors[p] = centers[par] + direction * half[par]
+        centers[p] = anchors[p] + direction * half[p]
+    scale = 0.33 / max(np.abs(centers).max() + half.max(), 1e-6)
+    centers *= scale; half *= scale; anchors *= scale
+
+    def sample(n, r):
+        part = r.integers(0, P, n)
+        face = r.integers(0, 6, n)
+        u = r.uniform(-1, 1, (n, 3))
+        ax = face % 3
+        u[np.arange(n), ax] = np.where(face < 3, -1.0, 1.0)
+        return centers[part] + u * half[part], part
+
+    cano, part = sample(N, rng)
+    theta = rng.uniform(-1, 1, (T, P))
+    pose = np.tile(np.eye(4), (T, P, 1, 1))
+    order = list(range(P))                                    # parents have smaller ids by construction
+    for t in range(T):
+        for p in order[1:]:
+            Rl = _rodrigues(axes[p], theta[t, p])
+            local = np.eye(4)
+            local[:3, :3] = Rl
+            local[:3, 3] = anchors[p] - Rl @ anchors[p]
+            pose[t, p] = pose[t, parent[p]] @ local
+    frames = np.zeros((T, M, 3))
+    for t in range(T):
+        pts, prt = sample(M, rng)
+        Rm = pose[t, prt, :3, :3]
+        frames[t] = np.einsum("nij,nj->ni", Rm, pts) + pose[t, prt, :3, 3] + rng.normal(0, noise, (M, 3))
+    return dict(cano=cano.astype(np.float32), part=part.astype(np.int64), frames=frames.astype(np.float32),
+                pose=pose.astype(np.float32), parent=parent, anchors=anchors.astype(np.float32),
+                axes=axes.astype(np.float32), theta=theta.astype(np.float32))

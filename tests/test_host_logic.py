@@ -1,0 +1,174 @@
+"""CPU: host-side logic and the C-ABI surface (no GPU compute)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "reart_b200.h")).read()
+    return sorted(set(re.findall(r"REART_API\s+[\w\s\*]+?\b(reart_\w+)\s*\(", src)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    import ctypes
+    from reart_b200 import _lib, build
+    so = build.build()
+    assert os.path.exists(so)
+    handle = ctypes.CDLL(so)
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(handle, s), f"{s} declared in include/reart_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes SIGNATURES out of sync with the header"
+    L = _lib.lib()
+    assert b"sm_100a" in L.reart_version()
+    assert L.reart_error_string(-2).decode().startswith("workspace")
+    assert L.reart_knn1_workspace_bytes(2, 100, 100) > 0 and L.reart_chamfer_workspace_bytes(1, 1, 1) > 0
+    assert L.reart_packed_bytes(1, 33) >= 64 * 12
+
+
+def test_header_cites_reference_for_every_entry_point():
+    src = open(os.path.join(ROOT, "include", "reart_b200.h")).read()
+    for name in ("utils/chamfer.py:174", "utils/chamfer.py:206", "networks/model.py:63-69", "networks/loss.py:24-29",
+                 "screw_se3/geo_utils.py:632-651", "screw_se3/screw_utils.py:6-30", "utils/kinematic_utils.py:151-198",
+                 "utils/flow_utils.py:147-170", "pointnet2_utils.py:29,263"):
+        assert name in src
+
+
+def test_cuda_sources_target_sm100a_and_use_tma_and_packed_math():
+    from reart_b200 import build
+    assert "arch=compute_100a,code=sm_100a" in " ".join(build.NVCC_FLAGS) and "-lineinfo" in build.NVCC_FLAGS
+    common = open(os.path.join(ROOT, "reart_b200", "csrc", "common.cuh")).read()
+    assert "cp.async.bulk.shared::cluster.global.mbarrier" in common and "fma.rn.f32x2" in common
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "reart_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            path = os.path.join(dirpath, f)
+            if f.endswith(".py"):
+                text = open(path).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", text, re.M), path
+                assert "libreart_oracle" not in text and "oracle/_build" not in text, path
+            elif f.endswith((".cu", ".cuh", ".h")):
+                for line in open(path):
+                    if line.lstrip().startswith("#include"):
+                        assert "oracle" not in line, path
+
+
+def test_chamfer_argument_validation_matches_reference():
+    from reart_b200 import ReartError
+    from reart_b200.chamfer import ChamferDistance, knn_gather, knn_points
+    cd = ChamferDistance()
+    a, b = torch.randn(2, 5, 3), torch.randn(2, 6, 3)
+    with pytest.raises(TypeError):
+        cd(a.numpy(), b)
+    with pytest.raises(ValueError, match="same batchsize"):
+        cd(a, torch.randn(3, 6, 3))
+    with pytest.raises(ValueError, match="same dimensionality"):
+        cd(a, torch.randn(2, 6, 2))
+    with pytest.raises(ValueError, match="Reduction"):
+        cd(a, b, reduction="max")
+    with pytest.raises(ValueError, match="same batch dimension"):
+        knn_points(a, torch.randn(3, 6, 3))
+    with pytest.raises(ValueError, match="same point dimension"):
+        knn_points(a, torch.randn(2, 6, 4))
+    with pytest.raises(ReartError):                     # CPU tensors: no fallback
+        cd(a, b)
+    x = torch.arange(24.0).reshape(2, 4, 3)
+    idx = torch.tensor([[[0], [3]], [[1], [1]]])
+    out = knn_gather(x, idx)
+    assert out.shape == (2, 2, 1, 3) and torch.equal(out[0, 1, 0], x[0, 3]) and torch.equal(out[1, 0, 0], x[1, 1])
+
+
+def test_flow_loss_matches_reference_golden():
+    from reart_b200.loss import flow_loss
+    g = load_golden("flow.npz")
+    gt, mask = torch.from_numpy(g["blended"]), torch.from_numpy(g["mask"])
+    for robust, lk, gk in ((False, "l_mse", "g_mse"), (True, "l_hub", "g_hub")):
+        pred = torch.from_numpy(g["pred"]).requires_grad_(True)
+        l = flow_loss(gt, pred, flow_mask_list=mask, robust=robust)
+        assert abs(l.item() - float(g[lk])) <= 1e-5 * float(g[lk])
+        l.backward()
+        np.testing.assert_allclose(pred.grad.numpy(), g[gk], rtol=1e-5, atol=1e-8)
+    l = flow_loss(gt, torch.from_numpy(g["pred"]))
+    assert abs(l.item() - float(g["l_nomask"])) <= 1e-5 * float(g["l_nomask"])
+
+
+def test_torch_restatements_of_screw_helpers_match_reference_golden():
+    from reart_b200 import screw_se3
+    g = load_golden("se3.npz")
+    l, m, th, d = (torch.from_numpy(g[k]) for k in ("l", "m", "theta", "d"))
+    expc = screw_se3.screw_param_to_exponential_coordinates(l, m, th, d)
+    np.testing.assert_allclose(expc.numpy(), g["expc"], rtol=1e-5, atol=1e-7)
+    M = screw_se3.transform_from_exponential_coordinates(expc)
+    np.testing.assert_allclose(M.numpy(), g["M"], rtol=1e-5, atol=2e-6)
+    inv = screw_se3.inverse_transformation(M)
+    np.testing.assert_allclose(torch.bmm(inv, M).numpy(), np.tile(np.eye(4, dtype=np.float32), (M.shape[0], 1, 1)), atol=2e-5)
+    R = torch.from_numpy(g["R"])
+    assert screw_se3.matrix_to_rotation_6d(R).shape == (R.shape[0], 6)
+
+
+def test_tree_flattening_and_model_state_dict_keys():
+    from reart_b200.kinematic import flatten_tree
+    from reart_b200.model import BaseModel, KinematicModel
+    g = load_golden("nao.npz")
+    order, parent, edge = g["katC_order"], g["katC_parent"], g["katC_edge"]
+    edge_index = {f"{c}_{parent[c]}": int(edge[c]) for c in range(len(order)) if parent[c] >= 0}
+    paths = {}
+    for c in range(len(order)):
+        path, x = [c], c
+        while parent[x] >= 0:
+            x = int(parent[x]); path.append(x)
+        paths[c] = path
+    o2, p2, e2 = flatten_tree(paths, [int(o) for o in order], edge_index)
+    assert np.array_equal(o2, order) and np.array_equal(p2, parent) and np.array_equal(e2, edge)
+    bm = BaseModel(num_parts=20, pose_len=9)
+    assert set(bm.state_dict()) == {"proposal_6d", "proposal_t", "joint_connection", "seg_head.model.0.weight",
+                                    "seg_head.model.0.bias", "seg_head.model.2.weight"}
+    assert bm.state_dict()["seg_head.model.0.weight"].shape == (128, 3, 1)
+    km = KinematicModel(pose_len=9, seg_part=torch.from_numpy(g["katC_seg_part"].astype(np.int64)),
+                        cano_pc=torch.zeros(4096, 3), knn=None, edge_index=edge_index, paths_to_base=paths,
+                        reverse_topo=[int(o) for o in order])
+    assert set(km.state_dict()) == {"axis_list", "moment_list", "theta_list"}
+    km2 = KinematicModel(pose_len=9, seg_part=torch.from_numpy(g["katC_seg_part"].astype(np.int64)),
+                         cano_pc=torch.zeros(4096, 3), knn=None, edge_index=edge_index, paths_to_base=paths,
+                         reverse_topo=[int(o) for o in order], load_distance=True, load_root_trans=True)
+    assert set(km2.state_dict()) == {"axis_list", "moment_list", "theta_list", "distance_list", "root_6d", "root_t"}
+
+
+def test_model_utils_small_helpers():
+    from reart_b200.model_utils import create_transformation, tau_cosine, th_with_zeros
+    x = torch.randn(5, 3, 4)
+    y = th_with_zeros(x)
+    assert y.shape == (5, 4, 4) and torch.equal(y[:, 3], torch.tensor([0.0, 0, 0, 1]).expand(5, 4))
+    T = create_transformation(torch.eye(3)[None].repeat(2, 1, 1), torch.ones(2, 3, 1))
+    assert T.shape == (2, 4, 4) and float(T[0, 3, 3]) == 1 and float(T[0, 0, 3]) == 1
+    assert tau_cosine(0, 100, 1.0, 5.0) == 5.0 and abs(tau_cosine(100, 100, 1.0, 5.0) - 1.0) < 1e-12
+
+
+def test_dropin_registers_the_three_native_module_names():
+    import sys
+    from reart_b200 import dropin
+    dropin.install(force=True)
+    assert hasattr(sys.modules["chamferdist"]._C, "knn_points_idx")
+    assert hasattr(sys.modules["chamferdist"]._C, "knn_points_backward")
+    assert sys.modules["knn_cuda"].KNN(k=3, transpose_mode=True).k == 3
+    assert hasattr(sys.modules["pointnet2_cuda"], "furthest_point_sampling_wrapper")
+    assert hasattr(sys.modules["pointnet2_cuda"], "ball_query_wrapper")
+    for k in ("chamferdist", "chamferdist._C", "knn_cuda", "pointnet2_cuda"):
+        sys.modules.pop(k, None)
+
+
+def test_synthetic_generator_is_deterministic_and_in_range():
+    from reart_b200.synth import make_sequence
+    a = make_sequence(4, 512, 5, seed=2); b = make_sequence(4, 512, 5, seed=2)
+    assert np.array_equal(a["cano"], b["cano"]) and np.array_equal(a["frames"], b["frames"])
+    assert a["cano"].shape == (512, 3) and a["frames"].shape == (4, 512, 3) and a["pose"].shape == (4, 5, 4, 4)
+    assert np.abs(a["cano"]).max() < 0.4
