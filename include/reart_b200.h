@@ -56,6 +56,13 @@ REART_API int reart_chamfer_bidir_fwd(const float* src, const float* tgt, int64_
                             int64_t* i_fwd, float* d_bwd, int64_t* i_bwd, void* workspace, int64_t workspace_bytes,
                             void* stream);
 
+/* The search stage of reart_chamfer_bidir_fwd alone (no packing, no index recovery): fills the merge keys
+ * keys_a [B,N] / keys_b [B,M] (uint64: dist_bits << 32 | arg-min chunk) from src [B,N,3] and the PACKED tgt.
+ * Exposed so benchmarks can time the dominant kernel in isolation; *col_chunk_pts receives the column-chunk
+ * width (host pointer, may be NULL). */
+REART_API int reart_chamfer_sym_search(const float* src, const float* tgt_packed, int64_t B, int64_t N, int64_t M,
+                                       uint64_t* keys_a, uint64_t* keys_b, int32_t* col_chunk_pts, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Backward of the K=1 search.
  * Replaces chamferdist._C.knn_points_backward(p1, p2, lengths1, lengths2, idx, grad_dists)

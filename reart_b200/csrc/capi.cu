@@ -125,6 +125,20 @@ int reart_chamfer_bidir_fwd(const float* src, const float* tgt, int64_t B, int64
     return launch_knn1_finalize(p, stream);
 }
 
+int reart_chamfer_sym_search(const float* src, const float* tgt_packed, int64_t B, int64_t N, int64_t M,
+                             uint64_t* keys_a, uint64_t* keys_b, int32_t* col_chunk_pts, void* stream_) {
+    if (B <= 0 || N <= 0 || M <= 0 || !fits_int(B) || !fits_int(padded_points(N)) || !fits_int(padded_points(M)))
+        return REART_ERR_INVALID_ARG;
+    if (!src || !tgt_packed || !keys_a || !keys_b) return REART_ERR_INVALID_ARG;
+    SymParams sp = {};
+    sp.a = src; sp.b_packed = tgt_packed;
+    sp.keys_a = reinterpret_cast<u64*>(keys_a); sp.keys_b = reinterpret_cast<u64*>(keys_b);
+    sp.B = (int)B; sp.na = (int)N; sp.nb = (int)M; sp.nb_pad = (int)padded_points(M);
+    int rc = launch_chamfer_sym(sp, static_cast<cudaStream_t>(stream_));
+    if (col_chunk_pts) *col_chunk_pts = sp.col_chunk_pts;
+    return rc;
+}
+
 int reart_knn1_bwd(const float* p1, const float* p2, const int64_t* idx, const float* grad_dists, int64_t B,
                    int64_t P1, int64_t P2, float* grad_p1, float* grad_p2, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);

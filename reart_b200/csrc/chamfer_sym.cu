@@ -184,8 +184,15 @@ static int launch_sym_r(SymParams& p, cudaStream_t stream) {
         cudaMemsetAsync(p.keys_b, 0xff, sizeof(u64) * (size_t)p.B * p.nb, stream) != cudaSuccess)
         return kErrLaunch;
     const size_t smem = (size_t)kSymStages * kSymTileBytes + (size_t)kSymStages * kSymWarps * kSymTilePoints * 4;
-    if (cudaFuncSetAttribute(chamfer_sym_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return kErrLaunch;
+    // opt in to > 48 KB dynamic shared memory once per device (not a stream operation; safe under graph capture)
+    static bool attr_done[64] = {};
+    int devid = 0;
+    cudaGetDevice(&devid);
+    if (devid < 0 || devid >= 64 || !attr_done[devid]) {
+        if (cudaFuncSetAttribute(chamfer_sym_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return kErrLaunch;
+        if (devid >= 0 && devid < 64) attr_done[devid] = true;
+    }
     chamfer_sym_kernel<R><<<(unsigned)items, kSymThreads, smem, stream>>>(p);
     REART_CHECK_LAUNCH();
     return kOk;

@@ -1,0 +1,145 @@
+"""The optimisation iteration of the reference's run scripts, B200-native.
+
+``RelaxationEngine.step`` is one pass of run_robot.py:154-221 for ``--model=base`` with the recon loss:
+seg MLP -> straight-through gumbel weights -> 6D -> R -> fused [skin -> bidirectional Chamfer -> sum -> backward]
+-> (multi-GPU: one all-reduce of the shared-parameter gradients) -> Adam.  The steady-state iteration is
+captured once in a CUDA graph (NCCL all-reduce included) and replayed, so neither Python nor the ~4 host syncs
+per iteration of the reference loop sit on the critical path.
+
+``KinematicEngine.step`` is the same for ``--model=kinematic`` (fused tree FK instead of the 6D proposals).
+Frames are sharded across ranks by ``DistContext``; per-frame parameters stay local to their rank.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .dist import DistContext, GradBucket
+from .model import BaseModel, KinematicModel
+
+
+class _EngineBase:
+    def __init__(self, ctx: Optional[DistContext], use_graph: bool):
+        self.ctx = ctx or DistContext()
+        self.use_graph = use_graph
+        self._graph = None
+        self._static_loss = None
+        self.iteration = 0
+
+    # subclasses: _iteration() -> loss tensor (local part), self.optimizer, self.bucket
+    def _run_iteration(self):
+        self.optimizer.zero_grad(set_to_none=False)
+        loss = self._iteration()
+        loss.backward()
+        if self.ctx.world_size > 1:
+            self.bucket.extra[0] = loss.detach()
+            self.bucket.all_reduce(self.ctx)
+            total = self.bucket.extra[0]
+        else:
+            total = loss.detach()
+        self.optimizer.step()
+        return total
+
+    def _capture(self):
+        # warm-up on a side stream (allocator, cuBLAS/cuDNN handles, NCCL communicator), then capture
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self._run_iteration()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.ctx.barrier()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._static_loss = self._run_iteration()
+        self._graph = g
+
+    def step(self, tau: Optional[float] = None) -> torch.Tensor:
+        """One optimisation iteration; returns the (all-rank) loss as a device tensor -- no host sync."""
+        if tau is not None:
+            self.tau.fill_(float(tau))
+        self.iteration += 1
+        if not self.use_graph:
+            return self._run_iteration()
+        if self._graph is None:
+            self._capture()
+        self._graph.replay()
+        return self._static_loss
+
+
+class RelaxationEngine(_EngineBase):
+    """Relaxation model (networks/model.py BaseModel) + recon loss, frame-sharded."""
+
+    def __init__(self, cano: torch.Tensor, frames: torch.Tensor, num_parts: int, ctx: Optional[DistContext] = None,
+                 trans_lr: float = 1e-2, seg_lr: float = 1e-3, weight_decay: float = 0.0, use_graph: bool = True,
+                 seed: int = 2):
+        super().__init__(ctx, use_graph)
+        dev = cano.device
+        lo, hi = self.ctx.frames(frames.shape[0])
+        self.frame_range = (lo, hi)
+        self.cano = cano.float().contiguous()
+        self.frames = frames[lo:hi].float().contiguous()          # local shard of the observed frames
+        self.frames_packed = ops.pack_cloud(self.frames)          # constant over the optimisation: packed once
+        torch.manual_seed(seed)                                    # identical init + gumbel draws on every rank
+        torch.cuda.manual_seed_all(seed)
+        self.model = BaseModel(num_parts=num_parts, pose_len=hi - lo).to(dev)
+        self.tau = torch.ones((), device=dev)
+        seg_params = [p for p in self.model.seg_head.parameters() if p.requires_grad]
+        self.optimizer = torch.optim.Adam(
+            [{"params": [self.model.proposal_6d, self.model.proposal_t], "lr": trans_lr},
+             {"params": seg_params, "lr": seg_lr}], lr=1e-3, weight_decay=weight_decay, capturable=use_graph)
+        self.bucket = GradBucket(seg_params, extra_scalars=1)
+        self.pairs_per_step_local = 2 * (hi - lo) * self.cano.shape[0] * self.frames.shape[1]
+
+    def _iteration(self):
+        seg, weight = self.model.weights(self.cano, tau=self.tau)
+        R, tr = self.model.pose()
+        loss, self.skinned = ops.skinned_chamfer_loss(self.cano, weight, R, tr, self.frames, self.frames_packed)
+        return loss
+
+
+class KinematicEngine(_EngineBase):
+    """Projection model (networks/model.py KinematicModel) + recon loss, frame-sharded.
+    axis/moment are shared (all-reduced); theta/distance/root pose are per frame."""
+
+    def __init__(self, model_kwargs: dict, seg_part: torch.Tensor, cano: torch.Tensor, frames: torch.Tensor,
+                 ctx: Optional[DistContext] = None, lr: float = 1e-2, weight_decay: float = 0.0,
+                 use_graph: bool = True):
+        super().__init__(ctx, use_graph)
+        from .knn_module import KNN
+        dev = cano.device
+        lo, hi = self.ctx.frames(frames.shape[0])
+        self.frame_range = (lo, hi)
+        self.cano = cano.float().contiguous()
+        self.frames = frames[lo:hi].float().contiguous()
+        self.frames_packed = ops.pack_cloud(self.frames)
+        kw = dict(model_kwargs)
+        for k in ("theta_list", "distance_list", "root_trans"):
+            if k in kw:
+                kw[k] = kw[k][lo:hi].clone()
+        self.model = KinematicModel(pose_len=hi - lo, seg_part=seg_part, cano_pc=self.cano,
+                                    knn=KNN(k=1, transpose_mode=True), **kw).to(dev)
+        self.tau = torch.ones((), device=dev)
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        self.optimizer = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, capturable=use_graph)
+        self.bucket = GradBucket([self.model.axis_list, self.model.moment_list], extra_scalars=1)
+        with torch.no_grad():                                       # constant label transfer
+            self.weight = F.one_hot(self.model._labels(self.model.cano_pc), num_classes=self.model.num_parts).float()
+        self.pairs_per_step_local = 2 * (hi - lo) * self.cano.shape[0] * self.frames.shape[1]
+
+    def _iteration(self):
+        trans = self.model.transforms()
+        loss, self.skinned = ops.skinned_chamfer_loss(self.cano, self.weight, trans[:, :, :3, :3].contiguous(),
+                                                      trans[:, :, :3, 3].contiguous(), self.frames,
+                                                      self.frames_packed)
+        return loss
+
+
+def tau_schedule(i: int, n_iter: int, start_tau: float, end_tau: float) -> float:
+    """utils/model_utils.py:33-37 as run_robot.py:86,157 uses it (cur_iter = i + 1)."""
+    return end_tau + (start_tau - end_tau) * (math.cos(math.pi * (i + 1) / n_iter) + 1.0) * 0.5

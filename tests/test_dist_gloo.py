@@ -1,0 +1,85 @@
+"""CPU, world_size 2 over gloo: the host-side multi-GPU logic (frame sharding, one-bucket gradient all-reduce,
+candidate selection).  The data path needs no collective -- frames are independent."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, T, N, P, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import oracle
+    from reart_b200.dist import DistContext, GradBucket, select_best_candidate
+    from reart_b200.synth import make_sequence
+    ctx = DistContext.from_env(backend="gloo")
+    seq = make_sequence(T=T, N=N, P=P, seed=2)
+    lo, hi = ctx.frames(T)
+    # energy of the local shard through the oracle (the checker stands in for the GPU kernels on CPU):
+    # skin with the GT poses, Chamfer both ways, backward to the SHARED weights W
+    W = np.eye(P, dtype=np.float32)[seq["part"]]
+    R = np.ascontiguousarray(seq["pose"][lo:hi, :, :3, :3]); tr = np.ascontiguousarray(seq["pose"][lo:hi, :, :3, 3]) + 0.01
+    sk = oracle.skin_fwd(seq["cano"], W, R, tr)
+    ch = oracle.chamfer_bidir_fwd_bwd(sk, seq["frames"][lo:hi])
+    gW, gR, gt = oracle.skin_bwd(seq["cano"], W, R, tr, ch["grad_src"])
+    shared = torch.nn.Parameter(torch.from_numpy(W.copy()))
+    shared.grad = torch.from_numpy(gW.copy())
+    bucket = GradBucket([shared], extra_scalars=1)
+    bucket.extra[0] = ch["loss"]
+    bucket.all_reduce(ctx)
+    best, energies = select_best_candidate(ctx, energy=float(ch["loss"]))
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), gW=shared.grad.numpy(), loss=float(bucket.extra[0]), lo=lo, hi=hi,
+             best=best, energies=np.array(energies), local_loss=ch["loss"])
+    ctx.barrier()
+    ctx.destroy()
+
+
+def test_shard_bounds_cover_all_frames():
+    from reart_b200.dist import shard_bounds
+    for T in (1, 7, 8, 9, 64):
+        for G in (1, 2, 3, 8):
+            spans = [shard_bounds(T, G, r) for r in range(G)]
+            assert spans[0][0] == 0 and spans[-1][1] == T
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(G - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_frame_sharding_reproduces_single_rank_energy(tmp_path):
+    import oracle
+    from reart_b200.synth import make_sequence
+    T, N, P = 6, 400, 4
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, T, N, P, str(tmp_path)), nprocs=world, join=True)
+    r0 = np.load(tmp_path / "rank0.npz"); r1 = np.load(tmp_path / "rank1.npz")
+    assert (int(r0["lo"]), int(r0["hi"]), int(r1["lo"]), int(r1["hi"])) == (0, 3, 3, 6)
+    # single-rank reference on all frames
+    seq = make_sequence(T=T, N=N, P=P, seed=2)
+    W = np.eye(P, dtype=np.float32)[seq["part"]]
+    R = np.ascontiguousarray(seq["pose"][:, :, :3, :3]); tr = np.ascontiguousarray(seq["pose"][:, :, :3, 3]) + 0.01
+    sk = oracle.skin_fwd(seq["cano"], W, R, tr)
+    ch = oracle.chamfer_bidir_fwd_bwd(sk, seq["frames"])
+    gW, _, _ = oracle.skin_bwd(seq["cano"], W, R, tr, ch["grad_src"])
+    for r in (r0, r1):
+        assert abs(float(r["loss"]) - ch["loss"]) <= 1e-5 * ch["loss"]              # summed over ranks
+        np.testing.assert_allclose(r["gW"], gW, rtol=1e-4, atol=1e-5 * np.abs(gW).max())
+    assert np.array_equal(r0["gW"], r1["gW"])                                       # all-reduce => identical
+    # candidate selection: both ranks agree on the argmin of the gathered energies
+    e = r0["energies"]
+    assert int(r0["best"]) == int(r1["best"]) == int(np.argmin(e))
+    np.testing.assert_allclose(e, [float(r0["local_loss"]), float(r1["local_loss"])])
