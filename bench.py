@@ -120,7 +120,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(gpu_index)], stdout=open(self.path, "w"),
+                                          "-lms", "20", "-i", str(gpu_index)], stdout=open(self.path, "w"),
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
