@@ -248,7 +248,7 @@ def main():
     skinned = engine.skinned.contiguous()
     def search():
         _lib.check(L.reart_chamfer_sym_search(_lib.ptr(skinned), _lib.ptr(engine.frames_packed), Tl, N, N,
-                                              _lib.ptr(keys_a), _lib.ptr(keys_b), None, _lib.stream_ptr()), "search")
+                                              _lib.ptr(keys_a), _lib.ptr(keys_b), None, 0, _lib.stream_ptr()), "search")
     for _ in range(2):
         search()
     reps = 5
@@ -271,7 +271,7 @@ def main():
     ms_ffma, ops_ffma = ops.fp32_probe(0, iters=2000, device=dev)
     ffma_tf = 2.0 * ops_ffma / (ms_ffma * 1e-3) / 1e12
     alg_bytes = Tl * (12.0 * (N + N) + 8.0 * (N + N))                 # read both clouds once, write both key arrays
-    roofline = {"bound": "fp32_fma", "kernel": "chamfer_sym_kernel<8>", "achieved": achieved_tf, "peak": peak_tf,
+    roofline = {"bound": "fp32_fma", "kernel": "chamfer_sym_kernel<8,1>", "achieved": achieved_tf, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "peak_source": f"SMs({props.multi_processor_count}) x 128 lanes x 2 x sm_max_mhz({sm_max_mhz:.0f}) from "
                                "MEASURED_PEAKS.json (it carries no FP32 entry; BASELINE.md section 3)",

@@ -25,7 +25,8 @@ SIGNATURES = {
     "reart_knn1_fwd": (_c_int, [_vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp, _c_i64, _vp]),
     "reart_chamfer_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i64]),
     "reart_chamfer_bidir_fwd": (_c_int, [_vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp, _vp, _vp, _c_i64, _vp]),
-    "reart_chamfer_sym_search": (_c_int, [_vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp, ctypes.POINTER(ctypes.c_int32), _vp]),
+    "reart_chamfer_sym_search": (_c_int, [_vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp, ctypes.POINTER(ctypes.c_int32), _c_int,
+                                          _vp]),
     "reart_knn1_bwd": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp]),
     "reart_chamfer_bidir_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp]),
     "reart_packed_bytes": (_c_i64, [_c_i64, _c_i64]),

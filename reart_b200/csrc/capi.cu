@@ -126,7 +126,7 @@ int reart_chamfer_bidir_fwd(const float* src, const float* tgt, int64_t B, int64
 }
 
 int reart_chamfer_sym_search(const float* src, const float* tgt_packed, int64_t B, int64_t N, int64_t M,
-                             uint64_t* keys_a, uint64_t* keys_b, int32_t* col_chunk_pts, void* stream_) {
+                             uint64_t* keys_a, uint64_t* keys_b, int32_t* col_chunk_pts, int variant, void* stream_) {
     if (B <= 0 || N <= 0 || M <= 0 || !fits_int(B) || !fits_int(padded_points(N)) || !fits_int(padded_points(M)))
         return REART_ERR_INVALID_ARG;
     if (!src || !tgt_packed || !keys_a || !keys_b) return REART_ERR_INVALID_ARG;
@@ -134,6 +134,7 @@ int reart_chamfer_sym_search(const float* src, const float* tgt_packed, int64_t 
     sp.a = src; sp.b_packed = tgt_packed;
     sp.keys_a = reinterpret_cast<u64*>(keys_a); sp.keys_b = reinterpret_cast<u64*>(keys_b);
     sp.B = (int)B; sp.na = (int)N; sp.nb = (int)M; sp.nb_pad = (int)padded_points(M);
+    sp.variant = variant;
     int rc = launch_chamfer_sym(sp, static_cast<cudaStream_t>(stream_));
     if (col_chunk_pts) *col_chunk_pts = sp.col_chunk_pts;
     return rc;

@@ -24,18 +24,33 @@
 
 namespace reart {
 
-constexpr int kSymTileChunks = 16;
-constexpr int kSymTilePoints = kSymTileChunks * kChunk;      // 512
-constexpr int kSymTileBytes = kSymTilePoints * 12;           // 6144
 constexpr int kSymStages = 3;
 constexpr int kSymThreads = 256;
 constexpr int kSymWarps = kSymThreads / 32;
 
-template <int R>
+// R  = A points per thread (registers); S = column sub-chunks per warp: the lane's R distances to a target are
+// folded in S groups of R/S, each group goes through its own REDUX, so a column chunk is 32*R/S consecutive A
+// points.  In-lane folds + REDUX count R per target for every S, but a REDUX costs ~4 issue slots on B200 (measured),
+// so S=1 is the production setting; S is also bounded by shared memory
+// (2 buffers x 8 warps x S x tile points x 4 B), which is why the tile shrinks as S grows.
+template <int R, int S>
+struct SymCfg {
+    static constexpr int kTileChunks = S <= 2 ? 16 : (S == 4 ? 8 : 4);
+    static constexpr int kTilePoints = kTileChunks * kChunk;
+    static constexpr int kTileBytes = kTilePoints * 12;
+    static constexpr int kColBufs = 2;
+    static constexpr int kColBufWords = kSymWarps * S * kTilePoints;
+    static constexpr size_t kSmem = (size_t)kSymStages * kTileBytes + (size_t)kColBufs * kColBufWords * 4;
+    static constexpr int kColChunkPts = 32 * R / S;
+};
+
+template <int R, int S>
 __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymParams p) {
+    using C = SymCfg<R, S>;
+    constexpr int RS = R / S;                                  // points per lane per sub-chunk
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // [stages][tile bytes] | [stages][warps][tile points] u32
-    unsigned* colmin = reinterpret_cast<unsigned*>(smem_raw + kSymStages * kSymTileBytes);
+    // [stages][tile bytes] | [2][warps][S][tile points] u32
+    unsigned* colmin = reinterpret_cast<unsigned*>(smem_raw + kSymStages * C::kTileBytes);
     __shared__ __align__(8) uint64_t full_bar[kSymStages];
 
     int item = blockIdx.x;
@@ -49,12 +64,13 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymPa
     const int qbase = qb * QB;
     const float* __restrict__ q = p.a + (int64_t)b * p.na * 3;
 
+    // register r = s*RS + rr holds A point  qbase + warp*32R + s*(32 RS) + lane*RS + rr
     u64 QX[R], QY[R], QZ[R];
     float best[R], prev[R];
     unsigned bch[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const int i = qbase + tid * R + r;
+        const int i = qbase + warp * (32 * R) + (r / RS) * (32 * RS) + lane * RS + (r % RS);
         float x = INFINITY, y = INFINITY, z = INFINITY;          // out-of-range rows never win a column
         if (i < p.na) { x = q[3 * i]; y = q[3 * i + 1]; z = q[3 * i + 2]; }
         QX[r] = pack2(x, x); QY[r] = pack2(y, y); QZ[r] = pack2(z, z);
@@ -65,10 +81,10 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymPa
     const int cps = (chunks_total + p.splits - 1) / p.splits;
     const int chunk0 = split * cps;
     const int nchunks = min(cps, chunks_total - chunk0);
-    const int ntiles = (nchunks + kSymTileChunks - 1) / kSymTileChunks;
+    const int ntiles = (nchunks + C::kTileChunks - 1) / C::kTileChunks;
     const float* __restrict__ tp = p.b_packed + (int64_t)b * p.nb_pad * 3 + (int64_t)chunk0 * kChunk * 3;
     u64* __restrict__ keys_col = p.keys_b + (int64_t)b * p.nb;
-    const unsigned colchunk_base = (unsigned)(qbase / (32 * R));
+    const unsigned colchunk_base = (unsigned)(qbase / C::kColChunkPts);
 
     if (tid == 0) {
 #pragma unroll
@@ -79,10 +95,10 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymPa
 
     auto issue = [&](int k) {
         const int st = k % kSymStages;
-        const int nch = min(kSymTileChunks, nchunks - k * kSymTileChunks);
+        const int nch = min(C::kTileChunks, nchunks - k * C::kTileChunks);
         const uint32_t bytes = (uint32_t)nch * kChunk * 12;
         mbar_expect_tx(&full_bar[st], bytes);
-        tma_bulk_g2s(smem_raw + st * kSymTileBytes, tp + (int64_t)k * kSymTilePoints * 3, bytes, &full_bar[st]);
+        tma_bulk_g2s(smem_raw + st * C::kTileBytes, tp + (int64_t)k * C::kTilePoints * 3, bytes, &full_bar[st]);
     };
     if (tid == 0) {
         for (int k = 0; k < min(kSymStages, ntiles); ++k) issue(k);
@@ -91,9 +107,10 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymPa
     for (int k = 0; k < ntiles; ++k) {
         const int st = k % kSymStages;
         mbar_wait(&full_bar[st], (uint32_t)((k / kSymStages) & 1));
-        const int nch = min(kSymTileChunks, nchunks - k * kSymTileChunks);
-        const float4* __restrict__ tile = reinterpret_cast<const float4*>(smem_raw + st * kSymTileBytes);
-        unsigned* __restrict__ cm_w = colmin + (st * kSymWarps + warp) * kSymTilePoints;
+        const int nch = min(C::kTileChunks, nchunks - k * C::kTileChunks);
+        const float4* __restrict__ tile = reinterpret_cast<const float4*>(smem_raw + st * C::kTileBytes);
+        unsigned* __restrict__ cbuf = colmin + (k & 1) * C::kColBufWords;
+        unsigned* __restrict__ cm_w = cbuf + warp * (S * C::kTilePoints);
         for (int c = 0; c < nch; ++c) {
             const float4* __restrict__ cg = tile + c * (kChunk / 4 * 3);
 #pragma unroll
@@ -102,24 +119,29 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymPa
                 const u64 X01 = pack2(X.x, X.y), X23 = pack2(X.z, X.w);
                 const u64 Y01 = pack2(Y.x, Y.y), Y23 = pack2(Y.z, Y.w);
                 const u64 Z01 = pack2(Z.x, Z.y), Z23 = pack2(Z.z, Z.w);
-                float c0, c1, c2, c3;
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    float a0, a1, a2, a3;
-                    unpack2(sqdist_pair(QX[r], QY[r], QZ[r], X01, Y01, Z01), a0, a1);
-                    unpack2(sqdist_pair(QX[r], QY[r], QZ[r], X23, Y23, Z23), a2, a3);
-                    best[r] = min3(best[r], a0, a1);
-                    best[r] = min3(best[r], a2, a3);
-                    if (r == 0) { c0 = a0; c1 = a1; c2 = a2; c3 = a3; }
-                    else { c0 = fminf(c0, a0); c1 = fminf(c1, a1); c2 = fminf(c2, a2); c3 = fminf(c3, a3); }
+                for (int s = 0; s < S; ++s) {
+                    float c0, c1, c2, c3;
+#pragma unroll
+                    for (int rr = 0; rr < RS; ++rr) {
+                        const int r = s * RS + rr;
+                        float a0, a1, a2, a3;
+                        unpack2(sqdist_pair(QX[r], QY[r], QZ[r], X01, Y01, Z01), a0, a1);
+                        unpack2(sqdist_pair(QX[r], QY[r], QZ[r], X23, Y23, Z23), a2, a3);
+                        best[r] = min3(best[r], a0, a1);
+                        best[r] = min3(best[r], a2, a3);
+                        if (rr == 0) { c0 = a0; c1 = a1; c2 = a2; c3 = a3; }
+                        else { c0 = fminf(c0, a0); c1 = fminf(c1, a1); c2 = fminf(c2, a2); c3 = fminf(c3, a3); }
+                    }
+                    const unsigned m0 = __reduce_min_sync(0xffffffffu, __float_as_uint(c0));
+                    const unsigned m1 = __reduce_min_sync(0xffffffffu, __float_as_uint(c1));
+                    const unsigned m2 = __reduce_min_sync(0xffffffffu, __float_as_uint(c2));
+                    const unsigned m3 = __reduce_min_sync(0xffffffffu, __float_as_uint(c3));
+                    if (lane == 0)
+                        *reinterpret_cast<uint4*>(cm_w + s * C::kTilePoints + c * kChunk + 4 * g) = make_uint4(m0, m1, m2, m3);
                 }
-                const unsigned m0 = __reduce_min_sync(0xffffffffu, __float_as_uint(c0));
-                const unsigned m1 = __reduce_min_sync(0xffffffffu, __float_as_uint(c1));
-                const unsigned m2 = __reduce_min_sync(0xffffffffu, __float_as_uint(c2));
-                const unsigned m3 = __reduce_min_sync(0xffffffffu, __float_as_uint(c3));
-                if (lane == 0) *reinterpret_cast<uint4*>(cm_w + c * kChunk + 4 * g) = make_uint4(m0, m1, m2, m3);
             }
-            const unsigned gid = (unsigned)(chunk0 + k * kSymTileChunks + c);
+            const unsigned gid = (unsigned)(chunk0 + k * C::kTileChunks + c);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 if (best[r] < prev[r]) bch[r] = gid;
@@ -128,31 +150,33 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymPa
         }
         __syncthreads();                                   // tile consumed, per-warp column minima complete
         if (tid == 0 && k + kSymStages < ntiles) issue(k + kSymStages);
-        // fold the 8 per-warp column arrays of this tile and merge into the global column keys
+        // fold the warps x S column arrays of this tile and merge into the global column keys; (warp, s) in
+        // increasing order is increasing A index, so a strict < keeps the lowest chunk on ties
         const int npts = nch * kChunk;
-        const int jbase = (chunk0 + k * kSymTileChunks) * kChunk;
+        const int jbase = (chunk0 + k * C::kTileChunks) * kChunk;
         for (int e = tid; e < npts; e += kSymThreads) {
             const int j = jbase + e;
             if (j < p.nb) {
-                unsigned m = colmin[(st * kSymWarps) * kSymTilePoints + e];
+                unsigned m = cbuf[e];
                 unsigned wbest = 0;
 #pragma unroll
-                for (int w = 1; w < kSymWarps; ++w) {
-                    const unsigned v = colmin[(st * kSymWarps + w) * kSymTilePoints + e];
-                    if (v < m) { m = v; wbest = (unsigned)w; }
+                for (int ws = 1; ws < kSymWarps * S; ++ws) {
+                    const unsigned v = cbuf[ws * C::kTilePoints + e];
+                    if (v < m) { m = v; wbest = (unsigned)ws; }
                 }
                 const u64 key = ((u64)m << 32) | (u64)(colchunk_base + wbest);
                 if (p.qblocks == 1) keys_col[j] = key;
                 else atomicMin(&keys_col[j], key);
             }
         }
-        // colmin[st] is rewritten no earlier than tile k+kSymStages, i.e. after >= 1 further __syncthreads
+        // cbuf (k & 1) is rewritten in tile k+2, after the __syncthreads of tile k+1 which every thread reaches
+        // only after finishing this fold
     }
 
     u64* __restrict__ keys_row = p.keys_a + (int64_t)b * p.na;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const int i = qbase + tid * R + r;
+        const int i = qbase + warp * (32 * R) + (r / RS) * (32 * RS) + lane * RS + (r % RS);
         if (i < p.na) {
             const u64 key = ((u64)__float_as_uint(best[r]) << 32) | (u64)bch[r];
             if (p.splits == 1) keys_row[i] = key;
@@ -161,19 +185,20 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymPa
     }
 }
 
-static int sym_choose_splits(int64_t B, int qblocks, int chunks_total) {
+static int sym_choose_splits(int64_t B, int qblocks, int chunks_total, int tile_chunks) {
     const int64_t want = 148 * 2 * 6;
     const int64_t base = B * qblocks;
     int s = (int)ceil_div(want, base > 0 ? base : 1);
-    const int max_s = std::max(1, chunks_total / (2 * kSymTileChunks));
+    const int max_s = std::max(1, chunks_total / (2 * std::max(tile_chunks, 16)));
     return std::max(1, std::min(s, max_s));
 }
 
-template <int R>
-static int launch_sym_r(SymParams& p, cudaStream_t stream) {
+template <int R, int S>
+static int launch_sym_rs(SymParams& p, cudaStream_t stream) {
+    using C = SymCfg<R, S>;
     p.qblocks = (int)ceil_div(p.na, R * kSymThreads);
-    p.splits = sym_choose_splits(p.B, p.qblocks, p.nb_pad / kChunk);
-    p.col_chunk_pts = 32 * R;
+    p.splits = sym_choose_splits(p.B, p.qblocks, p.nb_pad / kChunk, C::kTileChunks);
+    p.col_chunk_pts = C::kColChunkPts;
     const int64_t items = (int64_t)p.B * p.qblocks * p.splits;
     if (items <= 0) return kOk;
     if (items > 0x7fffffff) return kErrUnsupported;
@@ -183,21 +208,30 @@ static int launch_sym_r(SymParams& p, cudaStream_t stream) {
     if (p.qblocks > 1 && !p.keys_preset &&
         cudaMemsetAsync(p.keys_b, 0xff, sizeof(u64) * (size_t)p.B * p.nb, stream) != cudaSuccess)
         return kErrLaunch;
-    const size_t smem = (size_t)kSymStages * kSymTileBytes + (size_t)kSymStages * kSymWarps * kSymTilePoints * 4;
     // opt in to > 48 KB dynamic shared memory once per device (not a stream operation; safe under graph capture)
     static bool attr_done[64] = {};
     int devid = 0;
     cudaGetDevice(&devid);
     if (devid < 0 || devid >= 64 || !attr_done[devid]) {
-        if (cudaFuncSetAttribute(chamfer_sym_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(chamfer_sym_kernel<R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem) != cudaSuccess)
             return kErrLaunch;
         if (devid >= 0 && devid < 64) attr_done[devid] = true;
     }
-    chamfer_sym_kernel<R><<<(unsigned)items, kSymThreads, smem, stream>>>(p);
+    chamfer_sym_kernel<R, S><<<(unsigned)items, kSymThreads, C::kSmem, stream>>>(p);
     REART_CHECK_LAUNCH();
     return kOk;
 }
 
-int launch_chamfer_sym(SymParams& p, cudaStream_t stream) { return launch_sym_r<8>(p, stream); }
+int launch_chamfer_sym(SymParams& p, cudaStream_t stream) {
+    // Measured on B200 (profiles/r01_sym_variants.log, T=64 x 16k): S=1 3.70 ms, S=2 3.87, S=4 4.17, S=8 4.45 --
+    // a REDUX costs ~4 issue slots, so one REDUX per target (S=1, 256-point column chunks) is the fastest search
+    // even after paying for the wider index-recovery re-scan.
+    switch (p.variant) {
+        case 2: return launch_sym_rs<8, 2>(p, stream);
+        case 4: return launch_sym_rs<8, 4>(p, stream);
+        case 8: return launch_sym_rs<8, 8>(p, stream);
+        default: return launch_sym_rs<8, 1>(p, stream);
+    }
+}
 
 }  // namespace reart

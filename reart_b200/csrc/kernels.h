@@ -36,8 +36,9 @@ struct SymParams {
     unsigned long long* keys_b;   // [B, nb]  column keys (chunk = col_chunk_pts A-points)
     int B, na, nb, nb_pad;
     int qblocks, splits;          // filled by the launcher
-    int col_chunk_pts;            // filled by the launcher (32 * R)
+    int col_chunk_pts;            // filled by the launcher (32 * R / S)
     int keys_preset;
+    int variant;                  // 0 = default; 1/2/4/8 = number of column sub-chunks per warp (tuning)
 };
 
 int launch_pack_cloud(const float* pts, float* packed, int64_t B, int64_t P, cudaStream_t stream);

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kSkinThreads) skin_fwd_kernel(const float* __r
 int launch_skin_fwd(const float* cano, const float* W, const float* R, const float* tr, int64_t T, int64_t N, int64_t P,
                     float* out, float* out_packed, cudaStream_t stream) {
     if (T <= 0 || N <= 0) return kOk;
-    if (P <= 0 || P > 256) return kErrUnsupported;
+    if (P <= 0 || P > 32) return kErrUnsupported;
     const int64_t n_pad = out_packed ? padded_points(N) : N;
     dim3 grid((unsigned)ceil_div(n_pad, kSkinThreads), (unsigned)ceil_div(T, kSkinFramesPerBlock));
     const size_t smem = (size_t)kSkinFramesPerBlock * P * 12 * sizeof(float);
@@ -80,95 +80,161 @@ int launch_skin_fwd(const float* cano, const float* W, const float* R, const flo
 }
 
 // ----------------------------------------------------------------------------- backward
-// g [T,N,3] -> gW [N,P] (+=), gR [T,P,9] (+=), gtr [T,P,3] (+=); outputs must be zero on entry.
+// g [T,N,3] -> gW [N,P], gR [T,P,9], gtr [T,P,3]
 //   gW[n,p]  = sum_t g[t,n] . (R[t,p] c_n + tr[t,p])                (dense in p: straight-through grads)
-//   gR[t,p]  = sum_n W[n,p] g[t,n] c_n^T ;  gtr[t,p] = sum_n W[n,p] g[t,n]   (only where W != 0)
-// grid (ceil(N/128), ceil(T/8)).  gW partial sums over the block's 8 frames are kept in shared memory
-// ([128][P+1] floats) and added to global with one atomic per (n,p) per block; gR/gtr are reduced in
-// shared memory across the block's points, then one atomic per (t,p,k) per block.
-__global__ void __launch_bounds__(kSkinThreads) skin_bwd_kernel(const float* __restrict__ cano,
-                                                                const float* __restrict__ W,
-                                                                const float* __restrict__ R,
-                                                                const float* __restrict__ tr,
-                                                                const float* __restrict__ g, int T, int N, int P,
-                                                                float* __restrict__ gW, float* __restrict__ gR,
-                                                                float* __restrict__ gtr) {
-    extern __shared__ float sm[];
-    float* sm_tf = sm;                                         // [frames][P][12]
-    float* sm_acc = sm_tf + kSkinFramesPerBlock * P * 12;      // [frames][P][12] reduction of gR|gtr
-    float* sm_gw = sm_acc + kSkinFramesPerBlock * P * 12;      // [128][P+1]
-    const int t0 = blockIdx.y * kSkinFramesPerBlock;
-    const int nt = min(kSkinFramesPerBlock, T - t0);
-    for (int e = threadIdx.x; e < nt * P * 12; e += blockDim.x) {
-        const int f = e / (P * 12), rem = e - f * P * 12, p = rem / 12, k = rem - p * 12;
-        const int64_t tp = (int64_t)(t0 + f) * P + p;
-        sm_tf[e] = (k < 9) ? R[tp * 9 + k] : tr[tp * 3 + (k - 9)];
-        sm_acc[e] = 0.f;
-    }
-    __syncthreads();
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+//   gR[t,p]  = sum_n W[n,p] g[t,n] c_n^T ;  gtr[t,p] = sum_n W[n,p] g[t,n]
+// Two kernels, no shared-memory atomics:
+//   skin_bwd_w_kernel     one thread per point, loops over all frames, P accumulators in registers;
+//   skin_bwd_pose_kernel  the pose gradients as a skinny GEMM  W^T [P x N] . G [N x 12T],  G[n,(t,k)] = g (x) [c,1]
+//                         built on the fly: one thread per column (t,k), P accumulators in registers, the block's
+//                         W rows broadcast from shared memory; partial sums of each n-chunk merge with one
+//                         float atomic per (t,p,k) per block.
+constexpr int kBwdFrames = 8;
+
+constexpr int kBwdWPoints = 32;                              // points per block
+constexpr int kBwdWThreads = kBwdWPoints * kBwdFrames;       // 256: thread = (point, frame lane)
+
+template <int PMAX>
+__global__ void __launch_bounds__(kBwdWThreads) skin_bwd_w_kernel(const float* __restrict__ cano,
+                                                                  const float* __restrict__ R,
+                                                                  const float* __restrict__ tr,
+                                                                  const float* __restrict__ g, int T, int N, int P,
+                                                                  float* __restrict__ gW) {
+    extern __shared__ float sm_dyn[];
+    float* sm_tf = sm_dyn;                                    // [kBwdFrames][P][12]
+    float* sm_red = sm_dyn + kBwdFrames * P * 12;             // [kBwdFrames][kBwdWPoints][PMAX+1]
+    const int pl = threadIdx.x % kBwdWPoints, tl = threadIdx.x / kBwdWPoints;
+    const int n = blockIdx.x * kBwdWPoints + pl;
     const bool real = n < N;
     float cx = 0.f, cy = 0.f, cz = 0.f;
     if (real) { cx = cano[3 * n]; cy = cano[3 * n + 1]; cz = cano[3 * n + 2]; }
-    float* my_gw = sm_gw + threadIdx.x * (P + 1);
-    for (int p = 0; p < P; ++p) my_gw[p] = 0.f;
-    if (real) {
-        const float* __restrict__ w = W + (int64_t)n * P;
-        for (int f = 0; f < nt; ++f) {
-            const float* gg = g + ((int64_t)(t0 + f) * N + n) * 3;
+    float acc[PMAX];
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p) acc[p] = 0.f;
+    for (int t0 = 0; t0 < T; t0 += kBwdFrames) {
+        const int nt = min(kBwdFrames, T - t0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < nt * P * 12; e += blockDim.x) {
+            const int f = e / (P * 12), rem = e - f * P * 12, p = rem / 12, k = rem - p * 12;
+            const int64_t tp = (int64_t)(t0 + f) * P + p;
+            sm_tf[e] = (k < 9) ? R[tp * 9 + k] : tr[tp * 3 + (k - 9)];
+        }
+        __syncthreads();
+        if (real && tl < nt) {
+            const float* gg = g + ((int64_t)(t0 + tl) * N + n) * 3;
             const float gx = gg[0], gy = gg[1], gz = gg[2];
-            const float* tf = sm_tf + f * P * 12;
-            float* acc = sm_acc + f * P * 12;
-            for (int p = 0; p < P; ++p) {
-                const float* m = tf + p * 12;
-                const float vx = cx * m[0] + cy * m[1] + cz * m[2] + m[9];
-                const float vy = cx * m[3] + cy * m[4] + cz * m[5] + m[10];
-                const float vz = cx * m[6] + cy * m[7] + cz * m[8] + m[11];
-                my_gw[p] += gx * vx + gy * vy + gz * vz;
-                const float wp = __ldg(w + p);
-                if (wp != 0.f) {
-                    float* a = acc + p * 12;
-                    const float wx = wp * gx, wy = wp * gy, wz = wp * gz;
-                    atomicAdd(a + 0, wx * cx); atomicAdd(a + 1, wx * cy); atomicAdd(a + 2, wx * cz);
-                    atomicAdd(a + 3, wy * cx); atomicAdd(a + 4, wy * cy); atomicAdd(a + 5, wy * cz);
-                    atomicAdd(a + 6, wz * cx); atomicAdd(a + 7, wz * cy); atomicAdd(a + 8, wz * cz);
-                    atomicAdd(a + 9, wx); atomicAdd(a + 10, wy); atomicAdd(a + 11, wz);
+            const float* tf = sm_tf + tl * P * 12;
+#pragma unroll
+            for (int p = 0; p < PMAX; ++p) {
+                if (p < P) {
+                    const float* m = tf + p * 12;
+                    const float vx = cx * m[0] + cy * m[1] + cz * m[2] + m[9];
+                    const float vy = cx * m[3] + cy * m[4] + cz * m[5] + m[10];
+                    const float vz = cx * m[6] + cy * m[7] + cz * m[8] + m[11];
+                    acc[p] += gx * vx + gy * vy + gz * vz;
                 }
             }
         }
-        float* o = gW + (int64_t)n * P;
-        if (gridDim.y == 1) { for (int p = 0; p < P; ++p) o[p] = my_gw[p]; }
-        else { for (int p = 0; p < P; ++p) atomicAdd(o + p, my_gw[p]); }
     }
+    float* mine = sm_red + (tl * kBwdWPoints + pl) * (PMAX + 1);
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p) mine[p] = acc[p];
     __syncthreads();
-    for (int e = threadIdx.x; e < nt * P * 12; e += blockDim.x) {
-        const float v = sm_acc[e];
-        if (v != 0.f) {
-            const int f = e / (P * 12), rem = e - f * P * 12, p = rem / 12, k = rem - p * 12;
-            const int64_t tp = (int64_t)(t0 + f) * P + p;
-            if (k < 9) atomicAdd(gR + tp * 9 + k, v);
-            else atomicAdd(gtr + tp * 3 + (k - 9), v);
+    // thread (pl, tl) finishes parts p = tl, tl+8, ...: sum over the 8 frame lanes in a fixed order
+    if (real) {
+        for (int p = tl; p < P; p += kBwdFrames) {
+            float s = 0.f;
+#pragma unroll
+            for (int f = 0; f < kBwdFrames; ++f) s += sm_red[(f * kBwdWPoints + pl) * (PMAX + 1) + p];
+            gW[(int64_t)n * P + p] = s;
         }
     }
 }
 
+constexpr int kPoseThreads = 256;
+constexpr int kPoseChunk = 256;                               // points per block
+
+template <int PMAX>
+__global__ void __launch_bounds__(kPoseThreads) skin_bwd_pose_kernel(const float* __restrict__ cano,
+                                                                     const float* __restrict__ W,
+                                                                     const float* __restrict__ g, int T, int N, int P,
+                                                                     float* __restrict__ gR, float* __restrict__ gtr) {
+    extern __shared__ float sm[];
+    float* sW = sm;                                            // [kPoseChunk][PMAX]
+    float* sC = sm + kPoseChunk * PMAX;                        // [kPoseChunk][3]
+    const int n0 = blockIdx.x * kPoseChunk;
+    const int cnt = min(kPoseChunk, N - n0);
+    for (int e = threadIdx.x; e < cnt * PMAX; e += blockDim.x) {
+        const int i = e / PMAX, p = e - i * PMAX;
+        sW[e] = p < P ? W[(int64_t)(n0 + i) * P + p] : 0.f;
+    }
+    for (int e = threadIdx.x; e < cnt * 3; e += blockDim.x) sC[e] = cano[(int64_t)n0 * 3 + e];
+    __syncthreads();
+    const int col = blockIdx.y * blockDim.x + threadIdx.x;    // column (t,k) of G
+    if (col >= T * 12) return;
+    const int t = col / 12, k = col - t * 12;
+    const int kk = k < 9 ? k / 3 : k - 9;                     // component of g
+    const int l = k < 9 ? k % 3 : -1;                         // component of c (or the constant 1)
+    const float* __restrict__ gp = g + ((int64_t)t * N + n0) * 3 + kk;
+    float acc[PMAX];
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p) acc[p] = 0.f;
+    for (int i = 0; i < cnt; ++i) {
+        float v = gp[(int64_t)i * 3];
+        if (l >= 0) v *= sC[3 * i + l];
+        const float4* w4 = reinterpret_cast<const float4*>(sW + i * PMAX);
+#pragma unroll
+        for (int q = 0; q < PMAX / 4; ++q) {
+            const float4 w = w4[q];
+            acc[4 * q] += w.x * v; acc[4 * q + 1] += w.y * v; acc[4 * q + 2] += w.z * v; acc[4 * q + 3] += w.w * v;
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p) {
+        if (p < P && acc[p] != 0.f) {
+            const int64_t tp = (int64_t)t * P + p;
+            if (k < 9) atomicAdd(gR + tp * 9 + k, acc[p]);
+            else atomicAdd(gtr + tp * 3 + (k - 9), acc[p]);
+        }
+    }
+}
+
+template <int PMAX>
+static int launch_skin_bwd_p(const float* cano, const float* W, const float* R, const float* tr, const float* g,
+                             int64_t T, int64_t N, int64_t P, float* gW, float* gR, float* gtr, cudaStream_t stream) {
+    {
+        const size_t smem = ((size_t)kBwdFrames * P * 12 + (size_t)kBwdWThreads * (PMAX + 1)) * sizeof(float);
+        if (smem > 48 * 1024 &&
+            cudaFuncSetAttribute(skin_bwd_w_kernel<PMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return kErrUnsupported;
+        skin_bwd_w_kernel<PMAX><<<(unsigned)ceil_div(N, kBwdWPoints), kBwdWThreads, smem, stream>>>(
+            cano, R, tr, g, (int)T, (int)N, (int)P, gW);
+        REART_CHECK_LAUNCH();
+    }
+    {
+        const size_t smem = (size_t)kPoseChunk * (PMAX + 3) * sizeof(float);
+        dim3 grid((unsigned)ceil_div(N, kPoseChunk), (unsigned)ceil_div(T * 12, kPoseThreads));
+        skin_bwd_pose_kernel<PMAX><<<grid, kPoseThreads, smem, stream>>>(cano, W, g, (int)T, (int)N, (int)P, gR, gtr);
+        REART_CHECK_LAUNCH();
+    }
+    return kOk;
+}
+
 int launch_skin_bwd(const float* cano, const float* W, const float* R, const float* tr, const float* g, int64_t T,
                     int64_t N, int64_t P, float* gW, float* gR, float* gtr, cudaStream_t stream) {
-    if (P <= 0 || P > 256) return kErrUnsupported;
-    if (N * P > 0 && cudaMemsetAsync(gW, 0, sizeof(float) * (size_t)(N * P), stream) != cudaSuccess) return kErrLaunch;
+    if (P <= 0 || P > 32) return kErrUnsupported;
     if (T * P > 0) {
         if (cudaMemsetAsync(gR, 0, sizeof(float) * (size_t)(T * P * 9), stream) != cudaSuccess) return kErrLaunch;
         if (cudaMemsetAsync(gtr, 0, sizeof(float) * (size_t)(T * P * 3), stream) != cudaSuccess) return kErrLaunch;
     }
-    if (T <= 0 || N <= 0) return kOk;
-    dim3 grid((unsigned)ceil_div(N, kSkinThreads), (unsigned)ceil_div(T, kSkinFramesPerBlock));
-    const size_t smem = ((size_t)2 * kSkinFramesPerBlock * P * 12 + (size_t)kSkinThreads * (P + 1)) * sizeof(float);
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(skin_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return kErrUnsupported;
-    skin_bwd_kernel<<<grid, kSkinThreads, smem, stream>>>(cano, W, R, tr, g, (int)T, (int)N, (int)P, gW, gR, gtr);
-    REART_CHECK_LAUNCH();
-    return kOk;
+    if (N <= 0) return kOk;
+    if (T <= 0) {
+        if (cudaMemsetAsync(gW, 0, sizeof(float) * (size_t)(N * P), stream) != cudaSuccess) return kErrLaunch;
+        return kOk;
+    }
+    if (P <= 8) return launch_skin_bwd_p<8>(cano, W, R, tr, g, T, N, P, gW, gR, gtr, stream);
+    if (P <= 16) return launch_skin_bwd_p<16>(cano, W, R, tr, g, T, N, P, gW, gR, gtr, stream);
+    return launch_skin_bwd_p<32>(cano, W, R, tr, g, T, N, P, gW, gR, gtr, stream);
 }
 
 }  // namespace reart
