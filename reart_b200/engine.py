@@ -59,6 +59,13 @@ class _EngineBase:
             self._static_loss = self._run_iteration()
         self._graph = g
 
+    def release(self) -> None:
+        """Drop the captured graph.  Must happen before the NCCL process group is destroyed: tearing down a
+        communicator that a live CUDA graph still references blocks inside destroy_process_group()."""
+        self._graph = None
+        self._static_loss = None
+        torch.cuda.synchronize()
+
     def step(self, tau: Optional[float] = None) -> torch.Tensor:
         """One optimisation iteration; returns the (all-rank) loss as a device tensor -- no host sync."""
         if tau is not None:

@@ -172,3 +172,30 @@ def test_synthetic_generator_is_deterministic_and_in_range():
     assert np.array_equal(a["cano"], b["cano"]) and np.array_equal(a["frames"], b["frames"])
     assert a["cano"].shape == (512, 3) and a["frames"].shape == (4, 512, 3) and a["pose"].shape == (4, 5, 4, 4)
     assert np.abs(a["cano"]).max() < 0.4
+
+
+def test_unmodified_reference_chamfer_module_imports_over_the_dropin():
+    """Container-only (the GPU box has no reference tree): the reference's own utils/chamfer.py must import with
+    reart_b200.dropin providing `chamferdist._C`, and -- there being no CPU fallback -- fail loudly on CPU tensors."""
+    import importlib
+    import sys
+    ref_root = os.environ.get("REART_REFERENCE_ROOT", "/root/reference")
+    if not os.path.isdir(os.path.join(ref_root, "utils")):
+        pytest.skip("reference tree not present")
+    from reart_b200 import ReartError, dropin
+    saved = {k: sys.modules.pop(k, None) for k in ("chamferdist", "chamferdist._C", "knn_cuda", "pointnet2_cuda",
+                                                   "utils", "utils.chamfer")}
+    sys.path.insert(0, ref_root)
+    try:
+        dropin.install(force=True)
+        mod = importlib.import_module("utils.chamfer")
+        assert mod._C is sys.modules["chamferdist._C"]
+        with pytest.raises(ReartError):
+            mod.ChamferDistance()(torch.randn(1, 8, 3), torch.randn(1, 8, 3))
+    finally:
+        sys.path.remove(ref_root)
+        for k in ("chamferdist", "chamferdist._C", "knn_cuda", "pointnet2_cuda", "utils", "utils.chamfer"):
+            sys.modules.pop(k, None)
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
