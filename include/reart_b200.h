@@ -119,6 +119,24 @@ REART_API int reart_skinned_chamfer_fwd_bwd(const float* cano, const float* W, c
                                             int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Segmentation head and straight-through gumbel weights (the per-point, frame-independent part of an iteration).
+ * reart_segmlp_fwd/bwd replace MLPConv1d(3,(H,P)) = Conv1d(3,H,1,bias)+ReLU+Conv1d(H,P,1,no bias)
+ * (networks/blocks.py:99-118, built at networks/model.py:19, applied at :42-43): x [N,3], w0 [H,3], b0 [H],
+ * w2 [P,H] -> logits [N,P]; backward: glogits [N,P] -> gw0 [H,3], gb0 [H], gw2 [P,H] (overwritten).
+ * reart_gumbel_st_fwd/bwd replace F.gumbel_softmax(logits, tau, hard=True) (networks/model.py:44) given
+ * expo [N,P] ~ Exponential(1) drawn by torch and tau[1] on the device: -> W [N,P] (straight-through weights) and
+ * ysoft [N,P] (saved); backward: gW [N,P] -> glogits [N,P].   H <= 1024, P <= 32.
+ * ------------------------------------------------------------------------------------------- */
+REART_API int reart_segmlp_fwd(const float* x, const float* w0, const float* b0, const float* w2, int64_t N, int64_t H,
+                               int64_t P, float* logits, void* stream);
+REART_API int reart_segmlp_bwd(const float* x, const float* w0, const float* b0, const float* w2, const float* glogits,
+                               int64_t N, int64_t H, int64_t P, float* gw0, float* gb0, float* gw2, void* stream);
+REART_API int reart_gumbel_st_fwd(const float* logits, const float* expo, const float* tau, int64_t N, int64_t P,
+                                  float* W, float* ysoft, void* stream);
+REART_API int reart_gumbel_st_bwd(const float* ysoft, const float* tau, const float* gW, int64_t N, int64_t P,
+                                  float* glogits, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * 6D rotation representation -> matrix (Gram-Schmidt).
  * Replaces screw_se3/geo_utils.py:632-651 (rotation_6d_to_matrix); d6 [B,6] -> R [B,3,3].
  * Backward: gR [B,3,3] -> gd6 [B,6].

@@ -36,6 +36,10 @@ SIGNATURES = {
     "reart_energy_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i64]),
     "reart_skinned_chamfer_fwd_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _c_i64, _vp, _vp,
                                                _vp, _vp, _vp, _vp, _c_int, _vp, _c_i64, _vp]),
+    "reart_segmlp_fwd": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp]),
+    "reart_segmlp_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp, _vp]),
+    "reart_gumbel_st_fwd": (_c_int, [_vp, _vp, _vp, _c_i64, _c_i64, _vp, _vp, _vp]),
+    "reart_gumbel_st_bwd": (_c_int, [_vp, _vp, _vp, _c_i64, _c_i64, _vp, _vp]),
     "reart_rot6d_fwd": (_c_int, [_vp, _c_i64, _vp, _vp]),
     "reart_rot6d_bwd": (_c_int, [_vp, _vp, _c_i64, _vp, _vp]),
     "reart_screw_to_transform_fwd": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _vp, _vp]),

@@ -225,6 +225,46 @@ int reart_skinned_chamfer_fwd_bwd(const float* cano, const float* W, const float
     return launch_skin_bwd(cano, W, R, tr, gs, T, N, P, gW, gR, gtr, stream);
 }
 
+int reart_segmlp_fwd(const float* x, const float* w0, const float* b0, const float* w2, int64_t N, int64_t H, int64_t P,
+                     float* logits, void* stream_) {
+    if (N < 0 || H <= 0 || P <= 0) return REART_ERR_INVALID_ARG;
+    if (N == 0) return REART_OK;
+    if (!x || !w0 || !b0 || !w2 || !logits) return REART_ERR_INVALID_ARG;
+    return launch_segmlp(x, w0, b0, w2, nullptr, N, H, P, logits, nullptr, nullptr, nullptr,
+                         static_cast<cudaStream_t>(stream_));
+}
+
+int reart_segmlp_bwd(const float* x, const float* w0, const float* b0, const float* w2, const float* glogits, int64_t N,
+                     int64_t H, int64_t P, float* gw0, float* gb0, float* gw2, void* stream_) {
+    if (N < 0 || H <= 0 || P <= 0 || !gw0 || !gb0 || !gw2) return REART_ERR_INVALID_ARG;
+    if (N > 0 && (!x || !w0 || !b0 || !w2 || !glogits)) return REART_ERR_INVALID_ARG;
+    if (N == 0) {
+        cudaStream_t st = static_cast<cudaStream_t>(stream_);
+        if (cudaMemsetAsync(gw0, 0, sizeof(float) * (size_t)H * 3, st) != cudaSuccess) return REART_ERR_LAUNCH;
+        if (cudaMemsetAsync(gb0, 0, sizeof(float) * (size_t)H, st) != cudaSuccess) return REART_ERR_LAUNCH;
+        if (cudaMemsetAsync(gw2, 0, sizeof(float) * (size_t)H * P, st) != cudaSuccess) return REART_ERR_LAUNCH;
+        return REART_OK;
+    }
+    return launch_segmlp(x, w0, b0, w2, glogits, N, H, P, nullptr, gw0, gb0, gw2, static_cast<cudaStream_t>(stream_));
+}
+
+int reart_gumbel_st_fwd(const float* logits, const float* expo, const float* tau, int64_t N, int64_t P, float* W,
+                        float* ysoft, void* stream_) {
+    if (N < 0 || P <= 0) return REART_ERR_INVALID_ARG;
+    if (N == 0) return REART_OK;
+    if (!logits || !expo || !tau || !W || !ysoft) return REART_ERR_INVALID_ARG;
+    return launch_gumbel_st(logits, expo, tau, nullptr, N, P, W, ysoft, nullptr, static_cast<cudaStream_t>(stream_));
+}
+
+int reart_gumbel_st_bwd(const float* ysoft, const float* tau, const float* gW, int64_t N, int64_t P, float* glogits,
+                        void* stream_) {
+    if (N < 0 || P <= 0) return REART_ERR_INVALID_ARG;
+    if (N == 0) return REART_OK;
+    if (!ysoft || !tau || !gW || !glogits) return REART_ERR_INVALID_ARG;
+    return launch_gumbel_st(nullptr, nullptr, tau, gW, N, P, nullptr, const_cast<float*>(ysoft), glogits,
+                            static_cast<cudaStream_t>(stream_));
+}
+
 int reart_rot6d_fwd(const float* d6, int64_t B, float* R, void* stream_) {
     if (B < 0) return REART_ERR_INVALID_ARG;
     if (B == 0) return REART_OK;

@@ -108,6 +108,11 @@ int launch_fps(const float* xyz, int64_t B, int64_t N, int64_t m, int* out, cuda
 int launch_ball_query(const float* new_xyz, const float* xyz, int64_t B, int64_t N, int64_t m, float radius,
                       int nsample, int* idx, cudaStream_t stream);
 
+int launch_segmlp(const float* x, const float* w0, const float* b0, const float* w2, const float* glogits, int64_t N,
+                  int64_t H, int64_t P, float* logits, float* gw0, float* gb0, float* gw2, cudaStream_t stream);
+int launch_gumbel_st(const float* logits, const float* expo, const float* tau, const float* gW, int64_t N, int64_t P,
+                     float* W, float* ysoft, float* glogits, cudaStream_t stream);
+
 int launch_probe(int variant, int iters, int blocks, const float* in, float* out, double* ms, double* ops_per_thread,
                  cudaStream_t stream);
 

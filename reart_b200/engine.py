@@ -99,7 +99,7 @@ class RelaxationEngine(_EngineBase):
         seg_params = [p for p in self.model.seg_head.parameters() if p.requires_grad]
         self.optimizer = torch.optim.Adam(
             [{"params": [self.model.proposal_6d, self.model.proposal_t], "lr": trans_lr},
-             {"params": seg_params, "lr": seg_lr}], lr=1e-3, weight_decay=weight_decay, capturable=use_graph)
+             {"params": seg_params, "lr": seg_lr}], lr=1e-3, weight_decay=weight_decay, capturable=use_graph, fused=True)
         self.bucket = GradBucket(seg_params, extra_scalars=1)
         self.pairs_per_step_local = 2 * (hi - lo) * self.cano.shape[0] * self.frames.shape[1]
 
@@ -133,7 +133,7 @@ class KinematicEngine(_EngineBase):
                                     knn=KNN(k=1, transpose_mode=True), **kw).to(dev)
         self.tau = torch.ones((), device=dev)
         params = [p for p in self.model.parameters() if p.requires_grad]
-        self.optimizer = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, capturable=use_graph)
+        self.optimizer = torch.optim.Adam(params, lr=lr, weight_decay=weight_decay, capturable=use_graph, fused=True)
         self.bucket = GradBucket([self.model.axis_list, self.model.moment_list], extra_scalars=1)
         with torch.no_grad():                                       # constant label transfer
             self.weight = F.one_hot(self.model._labels(self.model.cano_pc), num_classes=self.model.num_parts).float()

@@ -34,10 +34,13 @@ class SegHead(nn.Module):
         return self.model(x)
 
     def logits(self, points: torch.Tensor) -> torch.Tensor:
-        """[N,3] -> [N,P]: the same k=1 convolutions written as two fp32 GEMMs (a 1x1 Conv1d IS a matmul).
-        Identical parameters/state_dict; avoids cuDNN's grouped wgrad kernel (2 % of an iteration at 16k points)
-        and cuDNN's default TF32, so the logits match the reference's CPU arithmetic to fp32 round-off."""
+        """[N,3] -> [N,P].  A k=1 Conv1d IS a per-point matmul: on CUDA the two layers run as one fused fp32 kernel
+        (forward and backward, csrc/segmlp.cu) on the conv parameters themselves -- identical state_dict; it also
+        avoids cuDNN's default TF32, so the logits match the reference's CPU arithmetic to fp32 round-off.
+        On CPU tensors the same math is two torch GEMMs (plain torch, no kernel of ours involved)."""
         w0, b0, w2 = self.model[0].weight[:, :, 0], self.model[0].bias, self.model[2].weight[:, :, 0]
+        if points.is_cuda:
+            return ops.seg_mlp(points, w0, b0, w2)
         h = torch.relu(torch.addmm(b0, points, w0.t()))
         return h @ w2.t()
 
@@ -90,6 +93,8 @@ class BaseModel(nn.Module):
     def weights(self, cano_pc, tau=1.0):
         """Straight-through gumbel-softmax assignment (networks/model.py:42-44); draws RNG every call."""
         seg = self.seg_logits(cano_pc)
+        if seg.is_cuda:
+            return seg, ops.gumbel_softmax_st(seg, tau)
         return seg, F.gumbel_softmax(seg, tau=tau, hard=True)
 
     def forward(self, cano_pc, **kwargs):

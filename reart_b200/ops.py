@@ -78,6 +78,79 @@ def skin(cano: torch.Tensor, W: torch.Tensor, R: torch.Tensor, tr: torch.Tensor)
     return _Skin.apply(cano, W, R, tr)
 
 
+# --------------------------------------------------------------------------------------- seg MLP + gumbel ST
+class _SegMlp(Function):
+    @staticmethod
+    def forward(ctx, x, w0, b0, w2):
+        _lib.require_cuda(x, w0, b0, w2)
+        L = _lib.lib()
+        xc, w0c, b0c, w2c = _f32c(x), _f32c(w0), _f32c(b0), _f32c(w2)
+        N, H, P = xc.shape[0], w0c.shape[0], w2c.shape[0]
+        logits = torch.empty(N, P, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(L.reart_segmlp_fwd(ptr(xc), ptr(w0c), ptr(b0c), ptr(w2c), N, H, P, ptr(logits), stream_ptr()),
+                  "reart_segmlp_fwd")
+        ctx.save_for_backward(xc, w0c, b0c, w2c)
+        return logits
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, w0, b0, w2 = ctx.saved_tensors
+        L = _lib.lib()
+        N, H, P = x.shape[0], w0.shape[0], w2.shape[0]
+        g = _f32c(g)
+        gw0, gb0, gw2 = torch.empty_like(w0), torch.empty_like(b0), torch.empty_like(w2)
+        with torch.cuda.device(x.device):
+            check(L.reart_segmlp_bwd(ptr(x), ptr(w0), ptr(b0), ptr(w2), ptr(g), N, H, P, ptr(gw0), ptr(gb0), ptr(gw2),
+                                     stream_ptr()), "reart_segmlp_bwd")
+        return None, gw0, gb0, gw2
+
+
+def seg_mlp(x, w0, b0, w2):
+    """logits = W2 relu(W0 x + b0): x [N,3] (no gradient), w0 [H,3], b0 [H], w2 [P,H] -> [N,P]."""
+    return _SegMlp.apply(x, w0, b0, w2)
+
+
+class _GumbelST(Function):
+    @staticmethod
+    def forward(ctx, logits, tau):
+        _lib.require_cuda(logits, tau)
+        L = _lib.lib()
+        lg = _f32c(logits)
+        N, P = lg.shape
+        expo = torch.empty_like(lg).exponential_()            # the same RNG draw F.gumbel_softmax makes
+        W = torch.empty_like(lg)
+        ysoft = torch.empty_like(lg)
+        with torch.cuda.device(lg.device):
+            check(L.reart_gumbel_st_fwd(ptr(lg), ptr(expo), ptr(tau), N, P, ptr(W), ptr(ysoft), stream_ptr()),
+                  "reart_gumbel_st_fwd")
+        ctx.save_for_backward(ysoft, tau)
+        return W
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gW):
+        ysoft, tau = ctx.saved_tensors
+        L = _lib.lib()
+        N, P = ysoft.shape
+        g = _f32c(gW)
+        out = torch.empty_like(ysoft)
+        with torch.cuda.device(ysoft.device):
+            check(L.reart_gumbel_st_bwd(ptr(ysoft), ptr(tau), ptr(g), N, P, ptr(out), stream_ptr()),
+                  "reart_gumbel_st_bwd")
+        return out, None
+
+
+def gumbel_softmax_st(logits: torch.Tensor, tau) -> torch.Tensor:
+    """F.gumbel_softmax(logits, tau=tau, hard=True) fused (networks/model.py:44); tau: float or 0-dim CUDA tensor."""
+    if not torch.is_tensor(tau):
+        tau = torch.full((1,), float(tau), dtype=torch.float32, device=logits.device)
+    else:
+        tau = tau.detach().to(device=logits.device, dtype=torch.float32).reshape(1)
+    return _GumbelST.apply(logits, tau)
+
+
 # --------------------------------------------------------------------------------------- 6D -> R
 class _Rot6d(Function):
     @staticmethod

@@ -7,7 +7,8 @@ r = csv.reader(lines); hdr = next(r); rows = list(r)
 ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
 names = [row[ki] for row in rows]; vals = [float(row[vi].replace(",", "")) for row in rows]
 sym = [i for i, n in enumerate(names) if "chamfer_sym" in n]
-a, b = (sym[-2], sym[-1]) if len(sym) >= 2 else (0, len(rows))
+k = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+a, b = (sym[-1 - k], sym[-k]) if len(sym) > k else (0, len(rows))
 agg = collections.OrderedDict()
 for i in range(a, b):
     n = names[i].split("(")[0][:72]

@@ -316,12 +316,13 @@ def test_base_model_kat_d(nao):
     hot = cu(g["katD_hot"].astype(np.int64))
     W[torch.arange(4096, device=dev()), hot] = cu(g["katD_hotval"])
     W.requires_grad_(True)
-    orig = F.gumbel_softmax
-    F.gumbel_softmax = lambda logits, tau=1.0, hard=False, **kw: W
+    from reart_b200 import ops
+    orig = ops.gumbel_softmax_st
+    ops.gumbel_softmax_st = lambda logits, tau: W          # inject the recorded draw (RNG differs CPU vs GPU)
     try:
         pc_trans, seg_arg, trans_list = model(cu(cano), tau=1.0)
     finally:
-        F.gumbel_softmax = orig
+        ops.gumbel_softmax_st = orig
     assert (seg_arg.cpu().numpy() == g["katD_seg_argmax"]).mean() > 0.999
     np.testing.assert_allclose(trans_list.detach().cpu().numpy(), g["katD_trans_list"], rtol=RTOL, atol=2e-6)
     np.testing.assert_allclose(pc_trans[:, ::16].detach().cpu().numpy(), g["katD_pc_trans_s16"], rtol=RTOL, atol=2e-6)
@@ -455,3 +456,47 @@ def test_cpu_tensors_fail_loudly():
     from reart_b200.chamfer import ChamferDistance
     with pytest.raises(ReartError):
         ChamferDistance()(torch.randn(1, 8, 3), torch.randn(1, 8, 3))
+
+
+# ----------------------------------------------------------------------------------------- fused seg MLP / gumbel
+@pytest.mark.parametrize("N,H,P", [(4096, 128, 20), (1000, 128, 15), (77, 64, 3), (5000, 128, 32)])
+def test_fused_seg_mlp_matches_torch(N, H, P):
+    from reart_b200 import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cpu").manual_seed(N + P)
+    x = (torch.rand(N, 3, generator=g) * 0.6 - 0.3).to(dev())
+    w0 = (torch.randn(H, 3, generator=g) * 2).to(dev()).requires_grad_(True)
+    b0 = torch.randn(H, generator=g).to(dev()).requires_grad_(True)
+    w2 = torch.randn(P, H, generator=g).to(dev()).requires_grad_(True)
+    coef = torch.randn(N, P, generator=g).to(dev())
+    ref = torch.relu(torch.addmm(b0, x, w0.t())) @ w2.t()
+    (ref * coef).sum().backward()
+    gref = [t.grad.clone() for t in (w0, b0, w2)]
+    for t in (w0, b0, w2):
+        t.grad = None
+    out = ops.seg_mlp(x, w0, b0, w2)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().cpu().numpy(), rtol=1e-5, atol=1e-5)
+    (out * coef).sum().backward()
+    for t, gr in zip((w0, b0, w2), gref):
+        np.testing.assert_allclose(t.grad.cpu().numpy(), gr.cpu().numpy(), rtol=1e-4, atol=1e-4 * float(gr.abs().max()))
+
+
+@pytest.mark.parametrize("tau", [1.0, 5.0, 0.5])
+def test_fused_gumbel_softmax_matches_torch_with_the_same_rng_stream(tau):
+    import torch.nn.functional as F
+    from reart_b200 import ops
+    N, P = 4096, 20
+    logits = (torch.randn(N, P, device=dev()) * 3).requires_grad_(True)
+    coef = torch.randn(N, P, device=dev())
+    torch.manual_seed(7)
+    ref = F.gumbel_softmax(logits, tau=tau, hard=True)
+    (ref * coef).sum().backward()
+    gref = logits.grad.clone(); logits.grad = None
+    torch.manual_seed(7)
+    W = ops.gumbel_softmax_st(logits, torch.tensor(tau, device=dev()))
+    assert (W.argmax(1) == ref.argmax(1)).float().mean() > 0.999          # same draw, same winners
+    same = W.argmax(1) == ref.argmax(1)
+    assert int((W != 0).sum()) == N and float((W[same] - ref.detach()[same]).abs().max()) < 1e-6   # zeros exact, ones 1 +- ulp
+    (W * coef).sum().backward()
+    np.testing.assert_allclose(logits.grad[same].cpu().numpy(), gref[same].cpu().numpy(), rtol=1e-4,
+                               atol=1e-5 * float(gref.abs().max()))
