@@ -45,7 +45,13 @@ class _EngineBase:
         return total
 
     def _capture(self):
-        # warm-up on a side stream (allocator, cuBLAS/cuDNN handles, NCCL communicator), then capture
+        """Warm up (allocator, library handles, NCCL communicator, lazily created Adam state), capture one
+        iteration, then put parameters, optimiser state and the RNG stream back where they were, so a graph
+        run is step-for-step the same optimisation as an eager run."""
+        params = [p for g in self.optimizer.param_groups for p in g["params"]]
+        snapshot = [p.detach().clone() for p in params]
+        dev = params[0].device
+        rng_state = torch.cuda.get_rng_state(dev)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -58,6 +64,15 @@ class _EngineBase:
         with torch.cuda.graph(g):
             self._static_loss = self._run_iteration()
         self._graph = g
+        with torch.no_grad():
+            for p, q in zip(params, snapshot):
+                p.copy_(q)
+            for st in self.optimizer.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()                              # step, exp_avg, exp_avg_sq (kept in place)
+        torch.cuda.set_rng_state(rng_state, dev)
+        torch.cuda.synchronize()
 
     def release(self) -> None:
         """Drop the captured graph.  Must happen before the NCCL process group is destroyed: tearing down a

@@ -500,3 +500,58 @@ def test_fused_gumbel_softmax_matches_torch_with_the_same_rng_stream(tau):
     (W * coef).sum().backward()
     np.testing.assert_allclose(logits.grad[same].cpu().numpy(), gref[same].cpu().numpy(), rtol=1e-4,
                                atol=1e-5 * float(gref.abs().max()))
+
+
+# ----------------------------------------------------------------------------------------- optimisation engines
+def test_relaxation_engine_graph_equals_eager_and_converges():
+    """run_robot.py:154-221 (--model=base, recon loss): the CUDA-graph replay must reproduce the eager iteration
+    (same seed => same gumbel draws) and the energy must go down."""
+    from reart_b200.engine import RelaxationEngine, tau_schedule
+    seq = synthetic_sequence(6, 2048, 5, seed=4)
+    cano, frames = cu(seq["cano"]), cu(seq["frames"])
+    losses = {}
+    for mode in (False, True):
+        eng = RelaxationEngine(cano, frames, num_parts=5, use_graph=mode, seed=2)
+        torch.manual_seed(11)
+        ls = []
+        for i in range(40):
+            ls.append(float(eng.step(tau_schedule(i, 200, 5.0, 1.0))))
+        losses[mode] = ls
+        assert eng.model.proposal_t.grad is not None and torch.isfinite(eng.model.proposal_t.grad).all()
+    np.testing.assert_allclose(losses[True][:5], losses[False][:5], rtol=2e-4)
+    assert np.mean(losses[True][-5:]) < 0.6 * np.mean(losses[True][:3])
+    assert np.mean(losses[False][-5:]) < 0.6 * np.mean(losses[False][:3])
+
+
+def test_kinematic_engine_recovers_joint_angles_on_a_synthetic_tree():
+    """--model=kinematic (networks/model.py:73-166): revolute chain with known screws; start from perturbed
+    angles and check the fused FK + skin + Chamfer iteration drives the energy down."""
+    from reart_b200.engine import KinematicEngine
+    rng = np.random.default_rng(3)
+    T, N, P = 5, 3000, 4
+    E = P - 1
+    # chain 0 <- 1 <- 2 <- 3 (part c hangs on c-1), axes through anchor points
+    axis = rng.standard_normal((E, 3)); axis /= np.linalg.norm(axis, axis=1, keepdims=True)
+    anchor = np.cumsum(np.full((E, 3), 0.08), axis=0) * np.array([1.0, 0.2, 0.1])
+    moment = np.cross(anchor, axis)                                   # m = q x l
+    theta_gt = rng.uniform(-0.8, 0.8, (T, E)).astype(np.float32)
+    order = np.arange(P, dtype=np.int32); parent = np.arange(-1, P - 1, dtype=np.int32); edge = np.arange(-1, P - 1, dtype=np.int32)
+    part = rng.integers(0, P, N)
+    cano = (rng.uniform(-0.04, 0.04, (N, 3)) + np.concatenate([[np.zeros(3)], anchor])[part] * 1.0).astype(np.float32)
+    poses = oracle.fk(axis, moment, theta_gt, None, order, parent, edge)
+    W = np.eye(P, dtype=np.float32)[part]
+    frames = oracle.skin_fwd(cano, W, poses[:, :, :3, :3], poses[:, :, :3, 3])
+    edge_index = {f"{c}_{c-1}": c - 1 for c in range(1, P)}
+    paths = {c: list(range(c, -1, -1)) for c in range(P)}
+    kw = dict(edge_index=edge_index, paths_to_base=paths, reverse_topo=list(range(P)),
+              axis_list=cu(axis.astype(np.float32)), moment_list=cu(moment.astype(np.float32)),
+              theta_list=cu(theta_gt + rng.normal(0, 0.15, theta_gt.shape).astype(np.float32)))
+    for mode in (False, True):
+        eng = KinematicEngine({k: (v.clone() if torch.is_tensor(v) else v) for k, v in kw.items()},
+                              torch.from_numpy(part), cu(cano), cu(frames), lr=1e-2, use_graph=mode)
+        first = float(eng.step())
+        for _ in range(150):
+            last = float(eng.step())
+        assert last < 0.2 * first, (mode, first, last)
+        err = (eng.model.theta_list.detach().cpu().numpy() - theta_gt)
+        assert np.abs(err).mean() < 0.06
