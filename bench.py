@@ -245,7 +245,7 @@ def main():
     # ---- roofline of the dominant kernel (chamfer_sym_kernel), timed alone with CUDA events on this stream
     Tl = hi - lo
     keys_a = torch.empty(Tl * N, dtype=torch.int64, device=dev); keys_b = torch.empty(Tl * N, dtype=torch.int64, device=dev)
-    skinned = engine.skinned.contiguous()
+    skinned = engine.skinned.detach().contiguous()
     def search():
         _lib.check(L.reart_chamfer_sym_search(_lib.ptr(skinned), _lib.ptr(engine.frames_packed), Tl, N, N,
                                               _lib.ptr(keys_a), _lib.ptr(keys_b), None, 0, _lib.stream_ptr()), "search")

@@ -99,8 +99,13 @@ class RelaxationEngine(_EngineBase):
 
     def __init__(self, cano: torch.Tensor, frames: torch.Tensor, num_parts: int, ctx: Optional[DistContext] = None,
                  trans_lr: float = 1e-2, seg_lr: float = 1e-3, weight_decay: float = 0.0, use_graph: bool = True,
-                 seed: int = 2):
+                 seed: int = 2, flow_ref=None, cano_idx: int = 0, lambda_flow: float = 1.0, robust_flow: bool = False):
+        """flow_ref: optional ``flow_utils.FlowReference`` (run_robot.py:78-84) enabling the flow loss of
+        run_robot.py:194-213 (single rank only: consecutive frames couple across shard boundaries)."""
         super().__init__(ctx, use_graph)
+        self.flow_ref, self.cano_idx, self.lambda_flow, self.robust_flow = flow_ref, cano_idx, lambda_flow, robust_flow
+        if flow_ref is not None and self.ctx.world_size > 1:
+            raise NotImplementedError("the flow loss couples frames t and t+1; it is supported on one rank only")
         dev = cano.device
         lo, hi = self.ctx.frames(frames.shape[0])
         self.frame_range = (lo, hi)
@@ -121,8 +126,22 @@ class RelaxationEngine(_EngineBase):
     def _iteration(self):
         seg, weight = self.model.weights(self.cano, tau=self.tau)
         R, tr = self.model.pose()
-        loss, self.skinned = ops.skinned_chamfer_loss(self.cano, weight, R, tr, self.frames, self.frames_packed)
+        loss, skinned = ops.skinned_chamfer_loss(self.cano, weight, R, tr, self.frames, self.frames_packed)
+        if self.flow_ref is not None:
+            loss = loss + self.lambda_flow * self._flow_term(skinned)
+        self.skinned = skinned.detach()                         # keep the cloud, not the autograd graph
         return loss
+
+    def _flow_term(self, pc_trans_list):
+        """run_robot.py:194-209: k=3 blended anchor flow (no grad, ONE launch for all pairs) vs predicted flow."""
+        from .flow_utils import blend_anchor_motion_batched
+        from .loss import flow_loss
+        c = self.cano_idx
+        complete = torch.cat((pc_trans_list[:c], self.cano[None], pc_trans_list[c:]), dim=0)
+        with torch.no_grad():
+            target_flow, mask = blend_anchor_motion_batched(complete[:-1].detach().contiguous(), self.flow_ref)
+        pred_flow = complete[1:] - complete[:-1]
+        return flow_loss(target_flow, pred_flow, flow_mask_list=mask, robust=self.robust_flow)
 
 
 class KinematicEngine(_EngineBase):
@@ -156,9 +175,9 @@ class KinematicEngine(_EngineBase):
 
     def _iteration(self):
         trans = self.model.transforms()
-        loss, self.skinned = ops.skinned_chamfer_loss(self.cano, self.weight, trans[:, :, :3, :3].contiguous(),
-                                                      trans[:, :, :3, 3].contiguous(), self.frames,
-                                                      self.frames_packed)
+        loss, skinned = ops.skinned_chamfer_loss(self.cano, self.weight, trans[:, :, :3, :3].contiguous(),
+                                                 trans[:, :, :3, 3].contiguous(), self.frames, self.frames_packed)
+        self.skinned = skinned.detach()
         return loss
 
 

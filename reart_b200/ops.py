@@ -352,20 +352,38 @@ class _SkinnedChamfer(Function):
                   "reart_skinned_chamfer_fwd_bwd")
         ctx.grads = (gW, gR, gtr)
         ctx.w_float = W.dtype.is_floating_point
-        ctx.mark_non_differentiable(skinned)
+        ctx.save_for_backward(cano_c, W_c, R_c, tr_c)
+        ctx.set_materialize_grads(False)                      # g_skinned stays None when nothing else consumes it
         return loss.to(torch.float32)[0], skinned
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, g_loss, _g_skinned):
+    def backward(ctx, g_loss, g_skinned):
         gW, gR, gtr = ctx.grads
         if gW is None:
             return None, None, None, None, None, None
-        return (None, gW * g_loss if ctx.w_float else None, gR * g_loss, gtr * g_loss, None, None)
+        if g_loss is None:
+            gW, gR, gtr = torch.zeros_like(gW), torch.zeros_like(gR), torch.zeros_like(gtr)
+        else:
+            gW, gR, gtr = gW * g_loss, gR * g_loss, gtr * g_loss
+        if g_skinned is not None:
+            # other consumers of the skinned cloud (flow / assign losses): one more skin backward, added by linearity
+            cano, W, R, tr = ctx.saved_tensors
+            L = _lib.lib()
+            T, P = R.shape[0], R.shape[1]
+            N = cano.shape[0]
+            g = _f32c(g_skinned)
+            eW, eR, et = torch.empty_like(W), torch.empty_like(R), torch.empty_like(tr)
+            with torch.cuda.device(cano.device):
+                check(L.reart_skin_bwd(ptr(cano), ptr(W), ptr(R), ptr(tr), ptr(g), T, N, P, ptr(eW), ptr(eR), ptr(et),
+                                       stream_ptr()), "reart_skin_bwd")
+            gW, gR, gtr = gW + eW, gR + eR, gtr + et
+        return (None, gW if ctx.w_float else None, gR, gtr, None, None)
 
 
 def skinned_chamfer_loss(cano, W, R, tr, tgt, tgt_packed=None):
-    """Fused recon_loss(model skin(cano), pc_list): returns (loss scalar, skinned [T,N,3] detached)."""
+    """Fused recon_loss(model skin(cano), pc_list): returns (loss scalar, skinned [T,N,3]).  `skinned` stays
+    differentiable for further consumers (flow / assign losses); their gradient costs one extra skin backward."""
     if tgt_packed is None:
         tgt_packed = pack_cloud(tgt)
     return _SkinnedChamfer.apply(cano, W, R, tr, tgt, tgt_packed)

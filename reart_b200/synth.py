@@ -65,3 +65,27 @@ def make_sequence(T: int, N: int, P: int, seed: int = 2, M: int | None = None, n
     return dict(cano=cano.astype(np.float32), part=part.astype(np.int64), frames=frames.astype(np.float32),
                 pose=pose.astype(np.float32), parent=parent, anchors=anchors.astype(np.float32),
                 axes=axes.astype(np.float32), theta=theta.astype(np.float32))
+
+
+def make_flow_reference(seq: dict, cano_idx: int = 0, n_ref: int | None = None, seed: int = 2, noise: float = 5e-4):
+    """Synthetic stand-in for the correspondence precompute of run_robot.py:75-84: for every consecutive pair of
+    the COMPLETE sequence (canonical frame inserted at cano_idx) a set of reference points on frame t and their
+    flow to frame t+1, obtained by posing canonical surface points with the ground-truth part poses.
+    Returns (pc_ref_list, flow_ref_list): lists of [n_t,3] float32 arrays with ragged n_t."""
+    rng = np.random.default_rng(seed + 17)
+    cano, part, pose = seq["cano"], seq["part"], seq["pose"]
+    T = pose.shape[0]
+    n_ref = n_ref or max(16, cano.shape[0] // 4)
+    ident = np.tile(np.eye(4, dtype=np.float32), (1, pose.shape[1], 1, 1))
+    complete = np.concatenate([pose[:cano_idx], ident, pose[cano_idx:]], axis=0)          # [T+1,P,4,4]
+    refs, flows = [], []
+    for t in range(T):
+        n = int(n_ref * rng.uniform(0.7, 1.0))
+        idx = rng.choice(cano.shape[0], n, replace=False)
+        def posed(k):
+            Rm = complete[k, part[idx], :3, :3]
+            return np.einsum("nij,nj->ni", Rm, cano[idx]) + complete[k, part[idx], :3, 3]
+        a, b = posed(t), posed(t + 1)
+        refs.append((a + rng.normal(0, noise, a.shape)).astype(np.float32))
+        flows.append((b - a + rng.normal(0, noise, a.shape)).astype(np.float32))
+    return refs, flows

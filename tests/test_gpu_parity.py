@@ -354,7 +354,7 @@ def test_fused_energy_equals_composed_path_and_oracle(T, N, P):
     Wt, Rt, trt = cu(W).requires_grad_(True), cu(R.astype(np.float32)).requires_grad_(True), cu(tr).requires_grad_(True)
     loss, skinned = ops.skinned_chamfer_loss(cu(cano), Wt, Rt, trt, cu(frames))
     loss.backward()
-    np.testing.assert_allclose(skinned.cpu().numpy(), sk_ref, rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(skinned.detach().cpu().numpy(), sk_ref, rtol=RTOL, atol=1e-6)
     assert abs(loss.item() - ch["loss"]) <= 2 * RTOL * ch["loss"]
     for got, want in ((Wt.grad, gW_ref), (Rt.grad, gR_ref), (trt.grad, gt_ref)):
         np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
@@ -555,3 +555,42 @@ def test_kinematic_engine_recovers_joint_angles_on_a_synthetic_tree():
         assert last < 0.2 * first, (mode, first, last)
         err = (eng.model.theta_list.detach().cpu().numpy() - theta_gt)
         assert np.abs(err).mean() < 0.06
+
+
+def test_recon_plus_flow_loss_fused_path_equals_composed_autograd():
+    """run_robot.py:189-213: recon + flow losses.  Fused energy (+ one extra skin backward for the flow term)
+    must give the same loss and gradients as the op-by-op autograd composition."""
+    from reart_b200 import ops
+    from reart_b200.chamfer import ChamferDistance
+    from reart_b200.flow_utils import FlowReference, blend_anchor_motion_batched
+    from reart_b200.loss import flow_loss, recon_loss
+    from reart_b200.synth import make_flow_reference
+    T, N, P = 5, 1500, 4
+    seq = synthetic_sequence(T, N, P, seed=6)
+    refs, flows = make_flow_reference(seq, cano_idx=2, n_ref=400)
+    ref = FlowReference([cu(r) for r in refs], [cu(f) for f in flows])
+    rng = np.random.default_rng(1)
+    W = np.eye(P, dtype=np.float32)[seq["part"]]
+    R = seq["pose"][:, :, :3, :3].copy(); tr = seq["pose"][:, :, :3, 3] + rng.normal(0, 0.01, (T, P, 3)).astype(np.float32)
+    cano, frames = cu(seq["cano"]), cu(seq["frames"])
+
+    def total(skinned):
+        complete = torch.cat((skinned[:2], cano[None], skinned[2:]), dim=0)
+        with torch.no_grad():
+            tf, mask = blend_anchor_motion_batched(complete[:-1].detach().contiguous(), ref)
+        return flow_loss(tf, complete[1:] - complete[:-1], flow_mask_list=mask)
+
+    grads = []
+    for fused in (True, False):
+        Wt, Rt, tt = cu(W).requires_grad_(True), cu(R).requires_grad_(True), cu(tr).requires_grad_(True)
+        if fused:
+            loss, skinned = ops.skinned_chamfer_loss(cano, Wt, Rt, tt, frames)
+        else:
+            skinned = ops.skin(cano, Wt, Rt, tt)
+            loss = recon_loss(skinned, frames, ChamferDistance())
+        loss = loss + 0.7 * total(skinned)
+        loss.backward()
+        grads.append((loss.item(), Wt.grad.clone(), Rt.grad.clone(), tt.grad.clone()))
+    assert abs(grads[0][0] - grads[1][0]) <= 1e-5 * abs(grads[1][0])
+    for a, b in zip(grads[0][1:], grads[1][1:]):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=1e-4 * float(b.abs().max()))
