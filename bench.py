@@ -31,6 +31,7 @@ WORKLOADS = {
     "cfg3_4k": (64, 4096, 15),
     "cfg3_64k": (64, 65536, 15),
     "cfg5": (64, 32768, 15),
+    "cfg3_16k_8f": (8, 16384, 15),    # one rank's shard of cfg3_16k at 8 GPUs (tuning aid)
     "tiny": (8, 2048, 6),
 }
 METRIC = "skinned_chamfer_fwd_bwd_directed_point_pairs_per_s"
@@ -280,6 +281,14 @@ def main():
                 "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": local_pairs,
                 "hbm_achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks.get("hbm_gbs"),
                 "traffic": None}
+    try:        # dram bytes of the same kernel from the committed ncu capture (only valid for the captured shape)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_sym_traffic.json")))
+        if tr.get("workload") == args.workload and tr.get("frames_per_launch") == Tl:
+            roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            roofline["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
+            roofline["algorithmic_bytes_per_launch"] = alg_bytes
+    except Exception:
+        pass
 
     line = None
     if ctx.is_main:

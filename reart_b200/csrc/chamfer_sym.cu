@@ -185,12 +185,28 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymPa
     }
 }
 
+// Number of target splits per (frame, query block).  CTAs map 1:1 to work items and two are resident per SM, so
+// the grid runs in waves of 2*148 CTAs: pick the split count whose item total wastes the least of its last wave
+// (strong scaling leaves few frames per GPU, where a bad count costs 15-25 % of the kernel), preferring fewer,
+// larger items on ties, and keeping at least one full tile (512 targets) per item.
 static int sym_choose_splits(int64_t B, int qblocks, int chunks_total, int tile_chunks) {
-    const int64_t want = 148 * 2 * 6;
-    const int64_t base = B * qblocks;
-    int s = (int)ceil_div(want, base > 0 ? base : 1);
-    const int max_s = std::max(1, chunks_total / (2 * std::max(tile_chunks, 16)));
-    return std::max(1, std::min(s, max_s));
+    const int64_t slots = 2 * 148;
+    const int64_t base = std::max<int64_t>(1, B * qblocks);
+    const int max_s = std::max(1, chunks_total / std::max(tile_chunks, 16));
+    if (base >= 8 * slots) return 1;                        // plenty of items already: tail < 1/8 wave
+    int best_s = 1;
+    double best_eff = -1.0;
+    for (int sp = 1; sp <= max_s; ++sp) {
+        const int64_t items = base * sp;
+        const int64_t waves = ceil_div(items, slots);
+        double eff = (double)items / (double)(waves * slots);
+        if (waves >= 8) eff = std::max(eff, 0.97);         // many waves: the tail no longer matters
+        // each item pays a fixed prologue/epilogue (~2 % of a 1024-target item): charge it
+        const double per_item_targets = (double)chunks_total * kChunk / sp;
+        eff *= per_item_targets / (per_item_targets + 24.0);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_s = sp; }
+    }
+    return best_s;
 }
 
 template <int R, int S>
