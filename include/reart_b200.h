@@ -59,7 +59,8 @@ REART_API int reart_chamfer_bidir_fwd(const float* src, const float* tgt, int64_
 /* The search stage of reart_chamfer_bidir_fwd alone (no packing, no index recovery): fills the merge keys
  * keys_a [B,N] / keys_b [B,M] (uint64: dist_bits << 32 | arg-min chunk) from src [B,N,3] and the PACKED tgt.
  * Exposed so benchmarks can time the dominant kernel in isolation; *col_chunk_pts receives the column-chunk
- * width (host pointer, may be NULL); variant 0 = production default, 1/2/4/8 = column sub-chunks per warp (tuning). */
+ * width (host pointer, may be NULL); variant 0 = production default; (variant % 16) in 1/2/4/8 = column sub-chunks per warp and
+ * (variant / 16) > 0 = forced number of target splits -- tuning knobs only. */
 REART_API int reart_chamfer_sym_search(const float* src, const float* tgt_packed, int64_t B, int64_t N, int64_t M,
                                        uint64_t* keys_a, uint64_t* keys_b, int32_t* col_chunk_pts, int variant,
                                        void* stream);

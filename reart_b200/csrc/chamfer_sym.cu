@@ -192,7 +192,9 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymPa
 static int sym_choose_splits(int64_t B, int qblocks, int chunks_total, int tile_chunks) {
     const int64_t slots = 2 * 148;
     const int64_t base = std::max<int64_t>(1, B * qblocks);
-    const int max_s = std::max(1, chunks_total / std::max(tile_chunks, 16));
+    // normally at least one full tile (512 targets) per item; when even that leaves SMs idle go down to 128 targets
+    int max_s = std::max(1, chunks_total / std::max(tile_chunks, 16));
+    if (base * max_s < slots) max_s = std::max(max_s, chunks_total / 4);
     if (base >= 8 * slots) return 1;                        // plenty of items already: tail < 1/8 wave
     int best_s = 1;
     double best_eff = -1.0;
@@ -214,6 +216,7 @@ static int launch_sym_rs(SymParams& p, cudaStream_t stream) {
     using C = SymCfg<R, S>;
     p.qblocks = (int)ceil_div(p.na, R * kSymThreads);
     p.splits = sym_choose_splits(p.B, p.qblocks, p.nb_pad / kChunk, C::kTileChunks);
+    if (p.variant >= 16) p.splits = std::max(1, std::min(p.variant / 16, p.nb_pad / kChunk));   // tuning override
     p.col_chunk_pts = C::kColChunkPts;
     const int64_t items = (int64_t)p.B * p.qblocks * p.splits;
     if (items <= 0) return kOk;
@@ -242,7 +245,7 @@ int launch_chamfer_sym(SymParams& p, cudaStream_t stream) {
     // Measured on B200 (profiles/r01_sym_variants.log, T=64 x 16k): S=1 3.70 ms, S=2 3.87, S=4 4.17, S=8 4.45 --
     // a REDUX costs ~4 issue slots, so one REDUX per target (S=1, 256-point column chunks) is the fastest search
     // even after paying for the wider index-recovery re-scan.
-    switch (p.variant) {
+    switch (p.variant % 16) {
         case 2: return launch_sym_rs<8, 2>(p, stream);
         case 4: return launch_sym_rs<8, 4>(p, stream);
         case 8: return launch_sym_rs<8, 8>(p, stream);

@@ -16,7 +16,7 @@ namespace reart {
 constexpr int kMlpThreads = 128;
 
 // ----------------------------------------------------------------------------- seg MLP forward
-// one thread per point; W0|b0 and W2^T staged in shared memory, every lane reads the same weights (broadcast)
+// W0|b0 and W2^T staged in shared memory (broadcast reads)
 template <int PMAX>
 __global__ void __launch_bounds__(kMlpThreads) segmlp_fwd_kernel(const float* __restrict__ x,
                                                                  const float* __restrict__ w0,
@@ -34,13 +34,16 @@ __global__ void __launch_bounds__(kMlpThreads) segmlp_fwd_kernel(const float* __
         s2[e] = p < P ? w2[p * H + k] : 0.f;
     }
     __syncthreads();
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const float px = x[3 * n], py = x[3 * n + 1], pz = x[3 * n + 2];
+    // 4 lanes per point, each covering a quarter of the hidden units; partial logits meet through two shuffles
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = gid >> 2, part = gid & 3;
+    const bool real = n < N;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (real) { px = x[3 * n]; py = x[3 * n + 1]; pz = x[3 * n + 2]; }
     float acc[PMAX];
 #pragma unroll
     for (int p = 0; p < PMAX; ++p) acc[p] = 0.f;
-    for (int k = 0; k < H; ++k) {
+    for (int k = part; k < H; k += 4) {
         const float4 w = reinterpret_cast<const float4*>(s0)[k];
         const float h = fmaxf(w.x * px + w.y * py + w.z * pz + w.w, 0.f);
         const float4* c4 = reinterpret_cast<const float4*>(s2 + k * PMAX);
@@ -51,14 +54,21 @@ __global__ void __launch_bounds__(kMlpThreads) segmlp_fwd_kernel(const float* __
         }
     }
 #pragma unroll
-    for (int p = 0; p < PMAX; ++p)
-        if (p < P) logits[(int64_t)n * P + p] = acc[p];
+    for (int p = 0; p < PMAX; ++p) {
+        acc[p] += __shfl_xor_sync(0xffffffffu, acc[p], 1);
+        acc[p] += __shfl_xor_sync(0xffffffffu, acc[p], 2);
+    }
+    if (real) {
+#pragma unroll
+        for (int p = 0; p < PMAX; ++p)
+            if (p < P && (p & 3) == part) logits[(int64_t)n * P + p] = acc[p];
+    }
 }
 
 // ----------------------------------------------------------------------------- seg MLP backward
 // thread = hidden unit k, block = chunk of points staged in shared memory; all sums over the chunk stay in
 // registers, one atomic per output element per block.  gw0 [H,3], gb0 [H], gw2 [P,H] must be zero on entry.
-constexpr int kMlpBwdChunk = 128;
+constexpr int kMlpBwdChunk = 64;
 
 template <int PMAX>
 __global__ void segmlp_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w0,
@@ -113,7 +123,7 @@ static int launch_segmlp_p(const float* x, const float* w0, const float* b0, con
     if (logits) {
         const size_t smem = (size_t)H * (4 + PMAX) * sizeof(float);
         if (smem > 48 * 1024) return kErrUnsupported;
-        segmlp_fwd_kernel<PMAX><<<(unsigned)ceil_div(N, kMlpThreads), kMlpThreads, smem, stream>>>(
+        segmlp_fwd_kernel<PMAX><<<(unsigned)ceil_div(4 * N, kMlpThreads), kMlpThreads, smem, stream>>>(
             x, w0, b0, w2, (int)N, (int)H, (int)P, logits);
         REART_CHECK_LAUNCH();
         return kOk;

@@ -24,10 +24,10 @@ __global__ void __launch_bounds__(kSkinThreads) skin_fwd_kernel(const float* __r
                                                                 const float* __restrict__ R,
                                                                 const float* __restrict__ tr, int T, int N, int P,
                                                                 float* __restrict__ out, float* __restrict__ out_packed,
-                                                                int n_pad) {
+                                                                int n_pad, int fpb) {
     extern __shared__ float sm_tf[];                          // [frames][P][12]: r00..r22, t0..t2
-    const int t0 = blockIdx.y * kSkinFramesPerBlock;
-    const int nt = min(kSkinFramesPerBlock, T - t0);
+    const int t0 = blockIdx.y * fpb;
+    const int nt = min(fpb, T - t0);
     for (int e = threadIdx.x; e < nt * P * 12; e += blockDim.x) {
         const int f = e / (P * 12), rem = e - f * P * 12, p = rem / 12, k = rem - p * 12;
         const int64_t tp = (int64_t)(t0 + f) * P + p;
@@ -71,10 +71,13 @@ int launch_skin_fwd(const float* cano, const float* W, const float* R, const flo
     if (T <= 0 || N <= 0) return kOk;
     if (P <= 0 || P > 32) return kErrUnsupported;
     const int64_t n_pad = out_packed ? padded_points(N) : N;
-    dim3 grid((unsigned)ceil_div(n_pad, kSkinThreads), (unsigned)ceil_div(T, kSkinFramesPerBlock));
-    const size_t smem = (size_t)kSkinFramesPerBlock * P * 12 * sizeof(float);
+    // frames per block: 8 amortises the W-row reads, but few frames (a GPU's shard under strong scaling) need more CTAs
+    int fpb = kSkinFramesPerBlock;
+    while (fpb > 1 && ceil_div(n_pad, kSkinThreads) * ceil_div(T, fpb) < 2 * 148) fpb /= 2;
+    dim3 grid((unsigned)ceil_div(n_pad, kSkinThreads), (unsigned)ceil_div(T, fpb));
+    const size_t smem = (size_t)fpb * P * 12 * sizeof(float);
     skin_fwd_kernel<<<grid, kSkinThreads, smem, stream>>>(cano, W, R, tr, (int)T, (int)N, (int)P, out, out_packed,
-                                                          (int)n_pad);
+                                                          (int)n_pad, fpb);
     REART_CHECK_LAUNCH();
     return kOk;
 }
@@ -152,7 +155,7 @@ __global__ void __launch_bounds__(kBwdWThreads) skin_bwd_w_kernel(const float* _
 }
 
 constexpr int kPoseThreads = 256;
-constexpr int kPoseChunk = 256;                               // points per block
+constexpr int kPoseChunk = 64;                                // points per block (more CTAs: the loop is latency bound)
 
 template <int PMAX>
 __global__ void __launch_bounds__(kPoseThreads) skin_bwd_pose_kernel(const float* __restrict__ cano,

@@ -32,7 +32,11 @@ class _EngineBase:
 
     # subclasses: _iteration() -> loss tensor (local part), self.optimizer, self.bucket
     def _run_iteration(self):
-        self.optimizer.zero_grad(set_to_none=False)
+        if getattr(self, "sink", None) is not None:
+            return self._run_iteration_sink()
+        # set_to_none: AccumulateGrad then adopts the fresh gradient tensors (no zero-fill and no add kernels); inside a
+        # captured graph their addresses are stable because they come from the graph's private pool
+        self.optimizer.zero_grad(set_to_none=True)
         loss = self._iteration()
         loss.backward()
         if self.ctx.world_size > 1:
@@ -41,6 +45,17 @@ class _EngineBase:
             total = self.bucket.extra[0]
         else:
             total = loss.detach()
+        self.optimizer.step()
+        return total
+
+    def _run_iteration_sink(self):
+        """Relaxation model: the seg-MLP backward writes into a flat bucket that also carries the loss and is
+        all-reduced in place from inside the backward (no pack/unpack copies around the collective)."""
+        self.optimizer.zero_grad(set_to_none=True)
+        loss = self._iteration()
+        self.sink.extra[0:1].copy_(loss.detach().reshape(1))
+        loss.backward()
+        total = self.sink.extra[0]
         self.optimizer.step()
         return total
 
@@ -120,7 +135,11 @@ class RelaxationEngine(_EngineBase):
         self.optimizer = torch.optim.Adam(
             [{"params": [self.model.proposal_6d, self.model.proposal_t], "lr": trans_lr},
              {"params": seg_params, "lr": seg_lr}], lr=1e-3, weight_decay=weight_decay, capturable=use_graph, fused=True)
-        self.bucket = GradBucket(seg_params, extra_scalars=1)
+        self.bucket = None
+        reducer = (lambda flat: self.ctx.all_reduce_sum_(flat)) if self.ctx.world_size > 1 else None
+        self.sink = ops.GradSink(self.model.seg_head.model[0].weight.shape[0], num_parts, dev, extra_scalars=1,
+                                 reducer=reducer)
+        self.model.seg_head.grad_sink = self.sink
         self.pairs_per_step_local = 2 * (hi - lo) * self.cano.shape[0] * self.frames.shape[1]
 
     def _iteration(self):

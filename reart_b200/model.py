@@ -40,7 +40,7 @@ class SegHead(nn.Module):
         On CPU tensors the same math is two torch GEMMs (plain torch, no kernel of ours involved)."""
         w0, b0, w2 = self.model[0].weight[:, :, 0], self.model[0].bias, self.model[2].weight[:, :, 0]
         if points.is_cuda:
-            return ops.seg_mlp(points, w0, b0, w2)
+            return ops.seg_mlp(points, w0, b0, w2, getattr(self, "grad_sink", None))
         h = torch.relu(torch.addmm(b0, points, w0.t()))
         return h @ w2.t()
 

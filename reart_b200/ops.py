@@ -81,7 +81,7 @@ def skin(cano: torch.Tensor, W: torch.Tensor, R: torch.Tensor, tr: torch.Tensor)
 # --------------------------------------------------------------------------------------- seg MLP + gumbel ST
 class _SegMlp(Function):
     @staticmethod
-    def forward(ctx, x, w0, b0, w2):
+    def forward(ctx, x, w0, b0, w2, sink):
         _lib.require_cuda(x, w0, b0, w2)
         L = _lib.lib()
         xc, w0c, b0c, w2c = _f32c(x), _f32c(w0), _f32c(b0), _f32c(w2)
@@ -91,6 +91,7 @@ class _SegMlp(Function):
             check(L.reart_segmlp_fwd(ptr(xc), ptr(w0c), ptr(b0c), ptr(w2c), N, H, P, ptr(logits), stream_ptr()),
                   "reart_segmlp_fwd")
         ctx.save_for_backward(xc, w0c, b0c, w2c)
+        ctx.sink = sink
         return logits
 
     @staticmethod
@@ -100,16 +101,41 @@ class _SegMlp(Function):
         L = _lib.lib()
         N, H, P = x.shape[0], w0.shape[0], w2.shape[0]
         g = _f32c(g)
-        gw0, gb0, gw2 = torch.empty_like(w0), torch.empty_like(b0), torch.empty_like(w2)
+        sink = ctx.sink
+        if sink is None:
+            gw0, gb0, gw2 = torch.empty_like(w0), torch.empty_like(b0), torch.empty_like(w2)
+        else:
+            # gradients land directly in the caller's flat bucket (multi-GPU: reduced in place, no pack/unpack copies)
+            flat = sink.flat
+            gw0 = flat[:3 * H].view(H, 3)
+            gb0 = flat[3 * H:4 * H]
+            gw2 = flat[4 * H:4 * H + P * H].view(P, H)
         with torch.cuda.device(x.device):
             check(L.reart_segmlp_bwd(ptr(x), ptr(w0), ptr(b0), ptr(w2), ptr(g), N, H, P, ptr(gw0), ptr(gb0), ptr(gw2),
                                      stream_ptr()), "reart_segmlp_bwd")
-        return None, gw0, gb0, gw2
+        if sink is not None:
+            sink.reduce()
+        return None, gw0, gb0, gw2, None
 
 
-def seg_mlp(x, w0, b0, w2):
+class GradSink:
+    """Flat gradient buffer of the seg MLP [w0 | b0 | w2 | extra scalars] plus the reduction to run on it once the
+    backward kernel has filled it (an NCCL all-reduce under frame sharding)."""
+
+    def __init__(self, H: int, P: int, device, extra_scalars: int = 1, reducer=None):
+        self.n_grad = 4 * H + P * H
+        self.flat = torch.zeros(self.n_grad + extra_scalars, dtype=torch.float32, device=device)
+        self.extra = self.flat[self.n_grad:]
+        self.reducer = reducer
+
+    def reduce(self):
+        if self.reducer is not None:
+            self.reducer(self.flat)
+
+
+def seg_mlp(x, w0, b0, w2, sink: "GradSink | None" = None):
     """logits = W2 relu(W0 x + b0): x [N,3] (no gradient), w0 [H,3], b0 [H], w2 [P,H] -> [N,P]."""
-    return _SegMlp.apply(x, w0, b0, w2)
+    return _SegMlp.apply(x, w0, b0, w2, sink)
 
 
 class _GumbelST(Function):
@@ -365,7 +391,7 @@ class _SkinnedChamfer(Function):
         if g_loss is None:
             gW, gR, gtr = torch.zeros_like(gW), torch.zeros_like(gR), torch.zeros_like(gtr)
         else:
-            gW, gR, gtr = gW * g_loss, gR * g_loss, gtr * g_loss
+            gW, gR, gtr = torch._foreach_mul([gW, gR, gtr], g_loss)          # one launch for the three
         if g_skinned is not None:
             # other consumers of the skinned cloud (flow / assign losses): one more skin backward, added by linearity
             cano, W, R, tr = ctx.saved_tensors
