@@ -597,3 +597,46 @@ def test_recon_plus_flow_loss_fused_path_equals_composed_autograd():
     assert abs(grads[0][0] - grads[1][0]) <= 1e-5 * abs(grads[1][0])
     for a, b in zip(grads[0][1:], grads[1][1:]):
         np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=1e-4 * float(b.abs().max()))
+
+
+def test_dropin_answers_the_reverse_search_from_the_symmetric_pass():
+    """The unmodified reference issues knn(src,tgt) then knn(tgt,src); the drop-in computes both in the first call."""
+    import sys
+    from reart_b200 import dropin
+    dropin.install(force=True)
+    C = sys.modules["chamferdist"]._C
+    rng = np.random.default_rng(12)
+    a = (rng.standard_normal((2, 700, 3)) * 0.3).astype(np.float32); b = (rng.standard_normal((2, 900, 3)) * 0.3).astype(np.float32)
+    ref = oracle.chamfer_bidir_fwd_bwd(a, b, want_grad=False)
+    A, Bt = cu(a), cu(b)
+    i1, d1 = C.knn_points_idx(A, Bt, None, None, 1, -1)
+    assert dropin._reverse_cache["sig"] is not None
+    i2, d2 = C.knn_points_idx(Bt, A, None, None, 1, -1)               # served from the cache
+    assert dropin._reverse_cache["sig"] is None
+    assert np.array_equal(i1[..., 0].cpu().numpy(), ref["i_fwd"]) and np.array_equal(d1[..., 0].cpu().numpy(), ref["d_fwd"])
+    assert np.array_equal(i2[..., 0].cpu().numpy(), ref["i_bwd"]) and np.array_equal(d2[..., 0].cpu().numpy(), ref["d_bwd"])
+    # a modified tensor (version bump) must NOT hit a stale entry
+    i1, d1 = C.knn_points_idx(A, Bt, None, None, 1, -1)
+    A.add_(0.01)
+    i3, d3 = C.knn_points_idx(Bt, A, None, None, 1, -1)
+    d_ref, i_ref = oracle.knn1(b, A.cpu().numpy())
+    assert np.array_equal(i3[..., 0].cpu().numpy(), i_ref) and np.array_equal(d3[..., 0].cpu().numpy(), d_ref)
+
+
+def test_snapshot_eval_helpers_match_reference_definitions(nao):
+    """utils/eval_utils.py: KD-tree Chamfer and N x N Rand index, restated here in numpy as the check."""
+    from reart_b200 import eval_utils
+    g, cano, pc_list = nao
+    a, b = pc_list[:3], pc_list[3:6]
+    want = 0.0
+    for x, y in zip(a, b):
+        dxy = ((x[:, None, :].astype(np.float64) - y[None]) ** 2).sum(-1)
+        want += dxy.min(1).sum() + dxy.min(0).sum()
+    got = eval_utils.compute_chamfer_list(a, b, reduction="sum")
+    assert abs(got - want) <= 1e-5 * want
+    gt = torch.from_numpy(g["gt_part"][2].astype(np.int64)); pd = torch.from_numpy(g["katA_part"].astype(np.int64))
+    s = int(max(gt.max(), pd.max())) + 1
+    G = torch.eye(s)[gt]; Pm = torch.eye(s)[pd]
+    ri_ref = ((G @ G.T) == (Pm @ Pm.T)).float().mean().item()
+    ri = eval_utils.eval_seg(gt.to(dev()), pd.to(dev()))
+    assert abs(float(ri) - ri_ref) < 1e-6
