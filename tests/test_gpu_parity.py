@@ -640,3 +640,26 @@ def test_snapshot_eval_helpers_match_reference_definitions(nao):
     ri_ref = ((G @ G.T) == (Pm @ Pm.T)).float().mean().item()
     ri = eval_utils.eval_seg(gt.to(dev()), pd.to(dev()))
     assert abs(float(ri) - ri_ref) < 1e-6
+
+
+def test_assign_loss_matches_the_run_script_formula():
+    """run_robot.py:164-187 restated with the oracle FPS + scipy Hungarian as the check."""
+    from scipy.optimize import linear_sum_assignment
+    from reart_b200.assign import AssignLoss
+    seq = synthetic_sequence(3, 512, 4, seed=9)
+    cano, frames = seq["cano"], seq["frames"]
+    skinned = frames + np.random.default_rng(0).normal(0, 0.01, frames.shape).astype(np.float32)
+    al = AssignLoss(cu(cano), cu(frames), downsample=4, assign_gap=5, lambda_assign=0.3)
+    S = cu(skinned).requires_grad_(True)
+    got = al(S)
+    got.backward()
+    n = 512 // 4
+    src_idx = oracle.fps(cano[None], n)[0]; tgt_idx = oracle.fps(frames, n)
+    want = 0.0
+    for t in range(3):
+        a = skinned[t][src_idx]; b = frames[t][tgt_idx[t]]
+        cost = np.sqrt(((a[:, None, :] - b[None]) ** 2).sum(-1))
+        r, c = linear_sum_assignment(cost)
+        want += ((a[r] - b[c]) ** 2).sum()
+    assert abs(got.item() - 0.3 * want) <= 1e-4 * 0.3 * want
+    assert S.grad is not None and int((S.grad.abs().sum(-1) > 0).sum()) == 3 * n
