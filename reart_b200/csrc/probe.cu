@@ -200,6 +200,36 @@ __global__ void __launch_bounds__(256) probe_kernel(const float* __restrict__ in
 #pragma unroll
         for (int r = 0; r < 8; ++r) acc += best[r];
     }
+    else if (V == 14 || V == 15 || V == 16) {
+        // FFMA2 x8 interleaved with: 14 two (compare + ballot), 15 two SHFL.BFLY, 16 two REDUX (reference for 12)
+        u64 p[8];
+        unsigned ub[2];
+        float fb[2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p[i] = pack2(a[2 * i], a[2 * i + 1]);
+        ub[0] = __float_as_uint(a[3]); ub[1] = __float_as_uint(a[7]); fb[0] = a[5]; fb[1] = a[9];
+        const u64 M = pack2(m, m), C = pack2(c, c + 1.f);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) p[i] = fma2(p[i], M, C);
+                if (V == 14) {
+                    ub[0] += __ballot_sync(0xffffffffu, ub[0] > ub[1] + (unsigned)u);
+                    ub[1] += __ballot_sync(0xffffffffu, ub[1] > ub[0] + 3u);
+                } else if (V == 15) {
+                    fb[0] += __shfl_xor_sync(0xffffffffu, fb[0], 16);
+                    fb[1] += __shfl_xor_sync(0xffffffffu, fb[1], 8);
+                } else {
+                    ub[0] = __reduce_min_sync(0xffffffffu, ub[0] + 1u);
+                    ub[1] = __reduce_min_sync(0xffffffffu, ub[1] + 3u);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) unpack2(p[i], a[2 * i], a[2 * i + 1]);
+        acc += __uint_as_float(ub[0]) + __uint_as_float(ub[1]) + fb[0] + fb[1];
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc += a[i];
     out[tid] = acc;
@@ -219,7 +249,8 @@ int launch_probe(int variant, int iters, int blocks, const float* in, float* out
             REART_PROBE_CASE(0, 64.0) REART_PROBE_CASE(1, 64.0) REART_PROBE_CASE(2, 32.0) REART_PROBE_CASE(3, 64.0)
             REART_PROBE_CASE(4, 64.0) REART_PROBE_CASE(5, 64.0) REART_PROBE_CASE(6, 64.0) REART_PROBE_CASE(7, 64.0)
             REART_PROBE_CASE(8, 64.0) REART_PROBE_CASE(9, 64.0) REART_PROBE_CASE(10, 64.0) REART_PROBE_CASE(11, 64.0)
-            REART_PROBE_CASE(12, 64.0) REART_PROBE_CASE(13, 64.0)
+            REART_PROBE_CASE(12, 64.0) REART_PROBE_CASE(13, 64.0) REART_PROBE_CASE(14, 64.0) REART_PROBE_CASE(15, 64.0)
+            REART_PROBE_CASE(16, 64.0)
 #undef REART_PROBE_CASE
             default: cudaEventDestroy(e0); cudaEventDestroy(e1); return kErrInvalidArg;
         }

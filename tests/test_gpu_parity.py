@@ -663,3 +663,24 @@ def test_assign_loss_matches_the_run_script_formula():
         want += ((a[r] - b[c]) ** 2).sum()
     assert abs(got.item() - 0.3 * want) <= 1e-4 * 0.3 * want
     assert S.grad is not None and int((S.grad.abs().sum(-1) > 0).sum()) == 3 * n
+
+
+def test_largest_named_size_256k_points_properties():
+    """BASELINE cfg3's largest cloud (N = M = 262 144) for one frame: the search must agree with a dense check on a
+    sample of rows/columns and with the one-direction kernel bit for bit."""
+    from reart_b200.chamfer import _ChamferBidir, knn_points
+    torch.manual_seed(1)
+    N = 262144
+    S = torch.rand(1, N, 3, device=dev()) * 0.6 - 0.3
+    T = torch.rand(1, N, 3, device=dev()) * 0.6 - 0.3
+    d_f, d_b, i_f, i_b = _ChamferBidir.apply(S, T)
+    assert int(i_f.max()) < N and int(i_b.max()) < N and int(i_f.min()) >= 0
+    sample = torch.arange(0, N, 4099, device=dev())
+    dense = ((S[:, sample, None, :] - T[:, None, :, :]) ** 2).sum(-1)
+    assert torch.allclose(dense.min(dim=2)[0], d_f[:, sample], rtol=1e-5, atol=1e-12)
+    dense_b = ((T[:, sample, None, :] - S[:, None, :, :]) ** 2).sum(-1)
+    assert torch.allclose(dense_b.min(dim=2)[0], d_b[:, sample], rtol=1e-5, atol=1e-12)
+    nb = torch.gather(S, 1, i_b[:, :, None].expand(-1, -1, 3))
+    assert torch.allclose(((T - nb) ** 2).sum(-1), d_b, rtol=1e-5, atol=1e-12)
+    one = knn_points(S[:, :20000].contiguous(), T, K=1)
+    assert torch.equal(one.idx[0, :, 0], i_f[0, :20000]) and torch.equal(one.dists[0, :, 0], d_f[0, :20000])
