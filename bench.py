@@ -30,6 +30,7 @@ WORKLOADS = {
     "cfg2": (16, 4096, 15),           # nao-shaped relaxation model
     "cfg3_4k": (64, 4096, 15),
     "cfg3_64k": (64, 65536, 15),
+    "cfg4": (32, 16384, 8),           # sapien-shaped kinematic projection model (KinematicEngine)
     "cfg5": (64, 32768, 15),
     "cfg3_16k_8f": (8, 16384, 15),    # one rank's shard of cfg3_16k at 8 GPUs (tuning aid)
     "tiny": (8, 2048, 6),
@@ -53,7 +54,8 @@ def parse_args():
 
 
 def config_dict(args, T, N, P, world):
-    return {"workload": f"{args.workload}: relaxation model (base, P={P}) synthetic sequence T={T} frames x "
+    kind = "kinematic projection model" if args.workload == "cfg4" else "relaxation model (base)"
+    return {"workload": f"{args.workload}: {kind}, P={P}, synthetic sequence T={T} frames x "
                         f"N=M={N} points, skin + bidirectional Chamfer recon loss fwd+bwd + Adam",
             "T": T, "N": N, "M": N, "P": P, "frames_per_gpu": T // max(world, 1) if args.scaling == "strong" else T,
             "partitioning": f"frames sharded over {world} rank(s), one all-reduce of shared grads per step",
@@ -185,7 +187,14 @@ def main():
     seq = make_sequence(T=T_total, N=N, P=P, seed=2)
     cano_h = torch.from_numpy(seq["cano"]).pin_memory()
     frames_h = torch.from_numpy(seq["frames"]).pin_memory()
-    engine = RelaxationEngine(cano_h.to(dev), frames_h.to(dev), num_parts=P, ctx=ctx, use_graph=not args.no_graph)
+    if args.workload == "cfg4":
+        from reart_b200.engine import KinematicEngine
+        from reart_b200.synth import kinematic_init
+        kw = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in kinematic_init(seq).items()}
+        engine = KinematicEngine(kw, torch.from_numpy(seq["part"]), cano_h.to(dev), frames_h.to(dev), ctx=ctx,
+                                 use_graph=not args.no_graph)
+    else:
+        engine = RelaxationEngine(cano_h.to(dev), frames_h.to(dev), num_parts=P, ctx=ctx, use_graph=not args.no_graph)
     lo, hi = engine.frame_range
     frames_local_h = frames_h[lo:hi]
     n_iter = 15000                                            # run_robot.py default; only shapes the tau schedule
@@ -305,7 +314,8 @@ def main():
                         "what": "pinned host cano+frames -> H2D -> pack -> full iteration -> loss D2H, per step"},
                 # our kernels per step and rank: segmlp fwd, gumbel fwd, rot6d fwd, skin fwd, chamfer_sym, energy bwd,
                 # skin bwd (w + pose), rot6d bwd, gumbel bwd, segmlp bwd
-                "gpu_launches": 11 * K, "cuda_graph": not args.no_graph,
+                # (kinematic model: fk fwd, skin fwd, chamfer_sym, energy bwd, skin bwd (w + pose), fk bwd)
+                "gpu_launches": (7 if args.workload == "cfg4" else 11) * K, "cuda_graph": not args.no_graph,
                 "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     # teardown: captured graphs reference the NCCL communicator, release them first; with more than one rank

@@ -89,3 +89,28 @@ def make_flow_reference(seq: dict, cano_idx: int = 0, n_ref: int | None = None, 
         refs.append((a + rng.normal(0, noise, a.shape)).astype(np.float32))
         flows.append((b - a + rng.normal(0, noise, a.shape)).astype(np.float32))
     return refs, flows
+
+
+def kinematic_init(seq: dict, theta_noise: float = 0.1, seed: int = 2):
+    """Screw parameters of the synthetic joint tree in the reference's KinematicModel convention
+    (networks/model.py:73-135): part p hangs on parent[p] by a revolute joint about `axes[p]` through `anchors[p]`
+    => l = axis / |axis|, m = anchor x l, theta[t, e] = joint angle.  Returns kwargs for KinematicModel /
+    KinematicEngine (numpy arrays; thetas perturbed by N(0, theta_noise)) and the part labels."""
+    rng = np.random.default_rng(seed + 31)
+    parent, axes, anchors, theta = seq["parent"], seq["axes"], seq["anchors"], seq["theta"]
+    P = len(parent)
+    l = axes / np.linalg.norm(axes, axis=1, keepdims=True)
+    edge_index, axis_list, moment_list, cols = {}, [], [], []
+    for p in range(1, P):
+        edge_index[f"{p}_{int(parent[p])}"] = p - 1
+        axis_list.append(l[p]); moment_list.append(np.cross(anchors[p], l[p])); cols.append(p)
+    paths = {}
+    for p in range(P):
+        path, x = [p], p
+        while parent[x] >= 0:
+            x = int(parent[x]); path.append(x)
+        paths[p] = path
+    th = theta[:, cols] + rng.normal(0, theta_noise, (theta.shape[0], P - 1))
+    return dict(edge_index=edge_index, paths_to_base=paths, reverse_topo=list(range(P)),
+                axis_list=np.asarray(axis_list, np.float32), moment_list=np.asarray(moment_list, np.float32),
+                theta_list=th.astype(np.float32))
