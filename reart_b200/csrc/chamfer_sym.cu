@@ -221,12 +221,18 @@ static int launch_sym_rs(SymParams& p, cudaStream_t stream) {
     const int64_t items = (int64_t)p.B * p.qblocks * p.splits;
     if (items <= 0) return kOk;
     if (items > 0x7fffffff) return kErrUnsupported;
-    if (p.splits > 1 && !p.keys_preset &&
-        cudaMemsetAsync(p.keys_a, 0xff, sizeof(u64) * (size_t)p.B * p.na, stream) != cudaSuccess)
-        return kErrLaunch;
-    if (p.qblocks > 1 && !p.keys_preset &&
-        cudaMemsetAsync(p.keys_b, 0xff, sizeof(u64) * (size_t)p.B * p.nb, stream) != cudaSuccess)
-        return kErrLaunch;
+    // merge keys start at +max wherever partial results meet through atomicMin; one memset when the two arrays are
+    // neighbours in the workspace (they are in every pipeline of capi.cu)
+    const bool need_a = p.splits > 1 && !p.keys_preset, need_b = p.qblocks > 1 && !p.keys_preset;
+    const size_t bytes_a = sizeof(u64) * (size_t)p.B * p.na, bytes_b = sizeof(u64) * (size_t)p.B * p.nb;
+    const char* a0 = reinterpret_cast<const char*>(p.keys_a);
+    const char* b0 = reinterpret_cast<const char*>(p.keys_b);
+    if (need_a && need_b && b0 >= a0 + bytes_a && (size_t)(b0 - a0) <= bytes_a + 4096) {
+        if (cudaMemsetAsync(p.keys_a, 0xff, (size_t)(b0 - a0) + bytes_b, stream) != cudaSuccess) return kErrLaunch;
+    } else {
+        if (need_a && cudaMemsetAsync(p.keys_a, 0xff, bytes_a, stream) != cudaSuccess) return kErrLaunch;
+        if (need_b && cudaMemsetAsync(p.keys_b, 0xff, bytes_b, stream) != cudaSuccess) return kErrLaunch;
+    }
     // opt in to > 48 KB dynamic shared memory once per device (not a stream operation; safe under graph capture)
     static bool attr_done[64] = {};
     int devid = 0;

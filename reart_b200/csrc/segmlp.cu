@@ -128,9 +128,13 @@ static int launch_segmlp_p(const float* x, const float* w0, const float* b0, con
         REART_CHECK_LAUNCH();
         return kOk;
     }
-    if (cudaMemsetAsync(gw0, 0, sizeof(float) * (size_t)H * 3, stream) != cudaSuccess) return kErrLaunch;
-    if (cudaMemsetAsync(gb0, 0, sizeof(float) * (size_t)H, stream) != cudaSuccess) return kErrLaunch;
-    if (cudaMemsetAsync(gw2, 0, sizeof(float) * (size_t)H * P, stream) != cudaSuccess) return kErrLaunch;
+    if (gb0 == gw0 + H * 3 && gw2 == gb0 + H) {                   // one flat [gw0 | gb0 | gw2] bucket: one memset
+        if (cudaMemsetAsync(gw0, 0, sizeof(float) * (size_t)H * (4 + P), stream) != cudaSuccess) return kErrLaunch;
+    } else {
+        if (cudaMemsetAsync(gw0, 0, sizeof(float) * (size_t)H * 3, stream) != cudaSuccess) return kErrLaunch;
+        if (cudaMemsetAsync(gb0, 0, sizeof(float) * (size_t)H, stream) != cudaSuccess) return kErrLaunch;
+        if (cudaMemsetAsync(gw2, 0, sizeof(float) * (size_t)H * P, stream) != cudaSuccess) return kErrLaunch;
+    }
     const size_t smem = (size_t)kMlpBwdChunk * (4 + PMAX) * sizeof(float);
     const int threads = (int)round_up(H, 32);
     segmlp_bwd_kernel<PMAX><<<(unsigned)ceil_div(N, kMlpBwdChunk), threads, smem, stream>>>(

@@ -227,8 +227,12 @@ int launch_skin_bwd(const float* cano, const float* W, const float* R, const flo
                     int64_t N, int64_t P, float* gW, float* gR, float* gtr, cudaStream_t stream) {
     if (P <= 0 || P > 32) return kErrUnsupported;
     if (T * P > 0) {
-        if (cudaMemsetAsync(gR, 0, sizeof(float) * (size_t)(T * P * 9), stream) != cudaSuccess) return kErrLaunch;
-        if (cudaMemsetAsync(gtr, 0, sizeof(float) * (size_t)(T * P * 3), stream) != cudaSuccess) return kErrLaunch;
+        if (gtr == gR + T * P * 9) {                              // one flat [gR | gtr] buffer: one memset
+            if (cudaMemsetAsync(gR, 0, sizeof(float) * (size_t)(T * P * 12), stream) != cudaSuccess) return kErrLaunch;
+        } else {
+            if (cudaMemsetAsync(gR, 0, sizeof(float) * (size_t)(T * P * 9), stream) != cudaSuccess) return kErrLaunch;
+            if (cudaMemsetAsync(gtr, 0, sizeof(float) * (size_t)(T * P * 3), stream) != cudaSuccess) return kErrLaunch;
+        }
     }
     if (N <= 0) return kOk;
     if (T <= 0) {

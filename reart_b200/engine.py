@@ -145,7 +145,7 @@ class RelaxationEngine(_EngineBase):
     def _iteration(self):
         seg, weight = self.model.weights(self.cano, tau=self.tau)
         R, tr = self.model.pose()
-        loss, skinned = ops.skinned_chamfer_loss(self.cano, weight, R, tr, self.frames, self.frames_packed)
+        loss, skinned = ops.skinned_chamfer_loss(self.cano, weight, R, tr, self.frames, self.frames_packed, unit_grad=True)
         if self.flow_ref is not None:
             loss = loss + self.lambda_flow * self._flow_term(skinned)
         self.skinned = skinned.detach()                         # keep the cloud, not the autograd graph
@@ -195,7 +195,8 @@ class KinematicEngine(_EngineBase):
     def _iteration(self):
         trans = self.model.transforms()
         loss, skinned = ops.skinned_chamfer_loss(self.cano, self.weight, trans[:, :, :3, :3].contiguous(),
-                                                 trans[:, :, :3, 3].contiguous(), self.frames, self.frames_packed)
+                                                 trans[:, :, :3, 3].contiguous(), self.frames, self.frames_packed,
+                                                 unit_grad=True)
         self.skinned = skinned.detach()
         return loss
 
