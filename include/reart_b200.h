@@ -207,6 +207,17 @@ REART_API int reart_ball_query(const float* new_xyz, const float* xyz, int64_t B
                                int nsample, int32_t* idx, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * One-shot all-reduce (sum, in place) of a small float bucket over NVLink peer memory -- the single collective of
+ * the frame-sharded iteration (the reference has no distributed code).
+ *   peer_base [world] (DEVICE array of uint64): base address of every rank's symmetric, peer-mapped allocation of
+ *     (2*n_pad floats + world uint32) zero-initialised bytes (e.g. torch.distributed._symmetric_memory);
+ *   epoch [1] uint32 on this device, zero-initialised, owned by this communicator; data [n] floats, n <= n_pad.
+ * Every rank must call it the same number of times; all ranks receive bitwise identical sums.
+ * ------------------------------------------------------------------------------------------- */
+REART_API int reart_allreduce_oneshot(const uint64_t* peer_base, int rank, int world, int64_t n, int64_t n_pad,
+                                      uint32_t* epoch, float* data, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * FP32-pipe micro-benchmark (roofline denominator).  Runs variant
  * 0..5 (see csrc/probe.cu) once warm and once timed with CUDA events on `stream`, SYNCHRONISES,
  * and returns milliseconds and the number of measured lane-operations per thread.

@@ -352,6 +352,15 @@ int reart_ball_query(const float* new_xyz, const float* xyz, int64_t B, int64_t 
     return launch_ball_query(new_xyz, xyz, B, N, m, radius, nsample, idx, static_cast<cudaStream_t>(stream_));
 }
 
+int reart_allreduce_oneshot(const uint64_t* peer_base, int rank, int world, int64_t n, int64_t n_pad, uint32_t* epoch,
+                            float* data, void* stream_) {
+    if (world < 1 || rank < 0 || rank >= world || n < 0 || n_pad < n) return REART_ERR_INVALID_ARG;
+    if (n == 0 || world == 1) return REART_OK;
+    if (!peer_base || !epoch || !data) return REART_ERR_INVALID_ARG;
+    return launch_allreduce_oneshot(reinterpret_cast<const unsigned long long*>(peer_base), rank, world, n, n_pad,
+                                    epoch, data, static_cast<cudaStream_t>(stream_));
+}
+
 int reart_fp32_probe(int variant, int iters, int blocks, const float* scratch_in, float* scratch_out, double* ms,
                      double* ops_per_thread, void* stream_) {
     return launch_probe(variant, iters, blocks, scratch_in, scratch_out, ms, ops_per_thread,

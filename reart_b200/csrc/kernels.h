@@ -113,6 +113,9 @@ int launch_segmlp(const float* x, const float* w0, const float* b0, const float*
 int launch_gumbel_st(const float* logits, const float* expo, const float* tau, const float* gW, int64_t N, int64_t P,
                      float* W, float* ysoft, float* glogits, cudaStream_t stream);
 
+int launch_allreduce_oneshot(const unsigned long long* peer_base, int rank, int world, int64_t n, int64_t n_pad,
+                             unsigned* epoch, float* data, cudaStream_t stream);
+
 int launch_probe(int variant, int iters, int blocks, const float* in, float* out, double* ms, double* ops_per_thread,
                  cudaStream_t stream);
 

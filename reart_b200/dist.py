@@ -115,6 +115,52 @@ class GradBucket:
         self.unpack()
 
 
+class OneShotAllReduce:
+    """In-place sum of a small float tensor across ranks through ``reart_allreduce_oneshot`` (peer memory over
+    NVLink).  Buffers come from torch's symmetric-memory allocator, which also exchanges the peer mappings.
+    Raises at construction if symmetric memory is unavailable -- callers fall back to NCCL."""
+
+    def __init__(self, ctx: DistContext, numel: int, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self._lib = _lib
+        self.ctx = ctx
+        self.n = int(numel)
+        self.n_pad = (self.n + 63) // 64 * 64
+        total = 2 * self.n_pad + max(64, ctx.world_size)
+        self.buf = symm_mem.empty(total, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD)
+        self.hdl = hdl
+        self.peer_base = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=device)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        ctx.barrier()                                            # every rank's flags are zero before anyone signals
+
+    def __call__(self, flat: torch.Tensor) -> torch.Tensor:
+        assert flat.is_contiguous() and flat.dtype == torch.float32 and flat.numel() == self.n
+        L = self._lib.lib()
+        with torch.cuda.device(flat.device):
+            self._lib.check(L.reart_allreduce_oneshot(self._lib.ptr(self.peer_base), self.ctx.rank, self.ctx.world_size,
+                                                      self.n, self.n_pad, self._lib.ptr(self.epoch), self._lib.ptr(flat),
+                                                      self._lib.stream_ptr()), "reart_allreduce_oneshot")
+        return flat
+
+
+def make_small_all_reduce(ctx: DistContext, numel: int, device):
+    """Best available in-place sum for a small bucket: the peer-memory one-shot kernel, else NCCL."""
+    if ctx.world_size <= 1:
+        return None
+    if ctx.backend == "nccl" and os.environ.get("REART_ONESHOT_ALLREDUCE", "1") != "0":
+        try:
+            return OneShotAllReduce(ctx, numel, device)
+        except Exception as exc:                                  # symmetric memory not available on this system
+            if ctx.is_main:
+                print(f"[reart_b200] one-shot all-reduce unavailable ({type(exc).__name__}: {exc}); using NCCL", flush=True)
+    return lambda flat: ctx.all_reduce_sum_(flat)
+
+
 def select_best_candidate(ctx: DistContext, energy: float, device=None) -> Tuple[int, List[float]]:
     """cano_idx candidate fits are independent runs, one per rank (README.md:60; energy = total_err,
     run_robot.py:314): gather the scalars and return (rank of the lowest energy, all energies)."""

@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .dist import DistContext, GradBucket
+from .dist import DistContext, GradBucket, make_small_all_reduce
 from .model import BaseModel, KinematicModel
 
 
@@ -136,9 +136,9 @@ class RelaxationEngine(_EngineBase):
             [{"params": [self.model.proposal_6d, self.model.proposal_t], "lr": trans_lr},
              {"params": seg_params, "lr": seg_lr}], lr=1e-3, weight_decay=weight_decay, capturable=use_graph, fused=True)
         self.bucket = None
-        reducer = (lambda flat: self.ctx.all_reduce_sum_(flat)) if self.ctx.world_size > 1 else None
-        self.sink = ops.GradSink(self.model.seg_head.model[0].weight.shape[0], num_parts, dev, extra_scalars=1,
-                                 reducer=reducer)
+        H = self.model.seg_head.model[0].weight.shape[0]
+        reducer = make_small_all_reduce(self.ctx, 4 * H + num_parts * H + 1, dev)
+        self.sink = ops.GradSink(H, num_parts, dev, extra_scalars=1, reducer=reducer)
         self.model.seg_head.grad_sink = self.sink
         self.pairs_per_step_local = 2 * (hi - lo) * self.cano.shape[0] * self.frames.shape[1]
 
