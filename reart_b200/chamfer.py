@@ -120,6 +120,26 @@ class ChamferDistance(torch.nn.Module):
     def __init__(self):
         super().__init__()
 
+    @staticmethod
+    def _validate(src, tgt, bidirectional, reverse, reduction):
+        """The checks of utils/chamfer.py:34-76 with the same exception types and messages (the reference's
+        TypeError path references an undefined name; here it reports the offending type)."""
+        for cloud in (src, tgt):
+            if not isinstance(cloud, torch.Tensor):
+                raise TypeError("Expected input type torch.Tensor. Got {} instead".format(type(cloud)))
+        if src.device != tgt.device:
+            raise ValueError(f"Source and target clouds must be on the same device. Got {src.device} and {tgt.device}.")
+        if src.shape[0] != tgt.shape[0]:
+            raise ValueError("Source and target pointclouds must have the same batchsize.")
+        if src.shape[2] != tgt.shape[2]:
+            raise ValueError("Source and target pointclouds must have the same dimensionality.")
+        if bidirectional and reverse:
+            warnings.warn("Both bidirectional and reverse set to True. bidirectional behavior takes precedence.")
+        if reduction not in ("sum", "mean"):
+            raise ValueError('Reduction must either be "sum" or "mean".')
+        if src.shape[2] != 3:
+            raise ValueError("reart_b200 kernels are specialised for 3-D points (D == 3).")
+
     def forward(
         self,
         source_cloud: torch.Tensor,
@@ -129,27 +149,7 @@ class ChamferDistance(torch.nn.Module):
         reduction: Optional[str] = "mean",
         return_index: Optional[bool] = False,
     ):
-        if not isinstance(source_cloud, torch.Tensor):
-            raise TypeError("Expected input type torch.Tensor. Got {} instead".format(type(source_cloud)))
-        if not isinstance(target_cloud, torch.Tensor):
-            raise TypeError("Expected input type torch.Tensor. Got {} instead".format(type(target_cloud)))
-        if source_cloud.device != target_cloud.device:
-            raise ValueError(
-                "Source and target clouds must be on the same device. "
-                f"Got {source_cloud.device} and {target_cloud.device}."
-            )
-        batchsize_source, lengths_source, dim_source = source_cloud.shape
-        batchsize_target, lengths_target, dim_target = target_cloud.shape
-        if batchsize_source != batchsize_target:
-            raise ValueError("Source and target pointclouds must have the same batchsize.")
-        if dim_source != dim_target:
-            raise ValueError("Source and target pointclouds must have the same dimensionality.")
-        if bidirectional and reverse:
-            warnings.warn("Both bidirectional and reverse set to True. bidirectional behavior takes precedence.")
-        if reduction != "sum" and reduction != "mean":
-            raise ValueError('Reduction must either be "sum" or "mean".')
-        if dim_source != 3:
-            raise ValueError("reart_b200 kernels are specialised for 3-D points (D == 3).")
+        self._validate(source_cloud, target_cloud, bidirectional, reverse, reduction)
 
         if bidirectional:
             d_f, d_b, i_f, i_b = _ChamferBidir.apply(source_cloud, target_cloud)

@@ -30,16 +30,15 @@ def tau_cosine(cur_iter, max_iter, end_temp, start_temp):
 
 
 def knn_query(query_pc, src_pc, src_input, knn):
-    """utils/model_utils.py:41-51 -- k-NN label / feature transfer from src_pc to query_pc."""
-    _, idx = knn(ref=src_pc.unsqueeze(dim=0), query=query_pc.unsqueeze(dim=0))
-    idx = idx.squeeze(dim=0).reshape(-1)
-    if len(src_input.shape) == 2:
-        target_seg = src_input[idx].reshape(src_input.shape[0], knn.k, src_input.shape[1])
-        return target_seg.mean(dim=1)
-    part_ids = src_input[idx].reshape(-1, knn.k)
-    if knn.k == 1:
-        return part_ids[:, 0]                      # torch.mode over one column is the column itself
-    return torch.mode(part_ids, dim=1)[0]
+    """utils/model_utils.py:41-51 -- transfer labels ([n] int) or features ([n,C]) from src_pc to query_pc through
+    the k nearest neighbours: features are averaged, labels take the mode (for k == 1 simply the neighbour's)."""
+    k = knn.k
+    nn_idx = knn(ref=src_pc[None], query=query_pc[None])[1][0].reshape(-1)        # [m*k]
+    picked = src_input[nn_idx]
+    if src_input.dim() == 2:
+        return picked.reshape(src_input.shape[0], k, src_input.shape[1]).mean(dim=1)
+    picked = picked.reshape(-1, k)
+    return picked[:, 0] if k == 1 else torch.mode(picked, dim=1)[0]
 
 
 def compute_pc_transform(cano_pc, pose_list, cano_part):

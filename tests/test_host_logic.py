@@ -199,3 +199,32 @@ def test_unmodified_reference_chamfer_module_imports_over_the_dropin():
         for k, v in saved.items():
             if v is not None:
                 sys.modules[k] = v
+
+
+def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
+    """Error behaviour at the boundary (include/reart_b200.h): negative codes, never exit(); the argument and
+    workspace checks run on the host before any CUDA call, so they are testable here."""
+    import ctypes
+    from reart_b200 import _lib
+    L = _lib.lib()
+    fake = ctypes.c_void_p(0x1000)                      # never dereferenced: every call below fails validation first
+    null = None
+    assert L.reart_knn1_fwd(null, null, 1, 4, 4, null, null, null, 0, null) == -1
+    assert L.reart_knn1_fwd(fake, fake, -1, 4, 4, fake, fake, fake, 0, null) == -1
+    assert L.reart_knn1_fwd(fake, fake, 1, 4, 4, fake, fake, null, 0, null) == -2          # no workspace
+    need = L.reart_knn1_workspace_bytes(1, 4, 4)
+    assert L.reart_knn1_fwd(fake, fake, 1, 4, 4, fake, fake, fake, 64, null) == -2         # too small
+    assert L.reart_chamfer_bidir_fwd(fake, fake, 2, 8, 8, fake, fake, fake, fake, fake, 16, null) == -2
+    assert L.reart_chamfer_bidir_fwd(null, fake, 2, 8, 8, fake, fake, fake, fake, fake, 1 << 20, null) == -1
+    assert L.reart_knn(fake, fake, 1, 10, 10, 9, fake, fake, null) == -1                   # k > 8
+    assert L.reart_knn(fake, fake, 1, 2, 10, 3, fake, fake, null) == -1                    # fewer refs than k
+    assert L.reart_fk_fwd(fake, fake, fake, null, null, null, null, null, 3, 4, fake, null) == -1
+    assert L.reart_skinned_chamfer_fwd_bwd(fake, fake, fake, fake, fake, fake, 2, 16, 16, 3, fake, fake, fake, fake,
+                                           fake, null, 1, fake, 8, null) == -2
+    assert L.reart_allreduce_oneshot(fake, 3, 2, 10, 12, fake, fake, null) == -1           # rank >= world
+    assert L.reart_knn1_workspace_bytes(-1, 1, 1) == -1
+    # empty problems are successes and touch nothing
+    assert L.reart_knn1_fwd(null, null, 0, 4, 4, null, null, null, 0, null) == 0
+    assert L.reart_skin_fwd(null, null, null, null, 0, 0, 3, null, null) == 0
+    for code in (0, -1, -2, -3, -4, -99):
+        assert len(L.reart_error_string(code)) > 0
