@@ -189,7 +189,8 @@ int reart_skin_bwd(const float* cano, const float* W, const float* R, const floa
 
 int64_t reart_energy_workspace_bytes(int64_t T, int64_t N, int64_t M) {
     if (T < 0 || N < 0 || M < 0) return -1;
-    return packed_bytes(T, N) + keys_bytes(T, N) + keys_bytes(T, M) + align_up(T * N * 12) + kAlign;
+    return align_up(T * round_up(N, 256) * 12) + keys_bytes(T, N) + keys_bytes(T, M) + align_up(T * N * 12) +
+           align_up(T * round_up(N, 256)) + kAlign;
 }
 
 int reart_skinned_chamfer_fwd_bwd(const float* cano, const float* W, const float* R, const float* tr, const float* tgt,
@@ -201,13 +202,16 @@ int reart_skinned_chamfer_fwd_bwd(const float* cano, const float* W, const float
         return REART_ERR_INVALID_ARG;
     if (!cano || !W || !R || !tr || !tgt || !tgt_packed || !skinned || !loss) return REART_ERR_INVALID_ARG;
     if (compute_grad && (!gW || !gR || !gtr)) return REART_ERR_INVALID_ARG;
+    // the skinned cloud's packed copy is x-sorted inside every 256-point column chunk (cheap index recovery)
+    const int64_t n_pad_sorted = round_up(N, 256);
     Carver ws(workspace, workspace_bytes);
-    float* psrc = ws.take<float>(T * packed_floats_per_batch(N));
+    float* psrc = ws.take<float>(T * n_pad_sorted * 3);
     u64* ka = ws.take<u64>(T * N);
     u64* kb = ws.take<u64>(T * M);
     float* gs = g_skinned ? g_skinned : ws.take<float>(T * N * 3);
+    unsigned char* perm = ws.take<unsigned char>(T * n_pad_sorted);
     if (!ws.ok) return REART_ERR_WORKSPACE;
-    int rc = launch_skin_fwd(cano, W, R, tr, T, N, P, skinned, psrc, stream);
+    int rc = launch_skin_fwd_sorted(cano, W, R, tr, T, N, P, skinned, psrc, perm, n_pad_sorted, stream);
     if (rc) return rc;
     SymParams sp = {};
     sp.a = skinned; sp.b_packed = tgt_packed; sp.keys_a = ka; sp.keys_b = kb;
@@ -215,11 +219,12 @@ int reart_skinned_chamfer_fwd_bwd(const float* cano, const float* W, const float
     rc = launch_chamfer_sym(sp, stream);
     if (rc) return rc;
     if (cudaMemsetAsync(loss, 0, sizeof(double), stream) != cudaSuccess) return REART_ERR_LAUNCH;
-    if (cudaMemsetAsync(gs, 0, sizeof(float) * (size_t)(T * N * 3), stream) != cudaSuccess) return REART_ERR_LAUNCH;
     EnergyParams ep = {};
     ep.src = skinned; ep.tgt = tgt; ep.src_packed = psrc; ep.tgt_packed = tgt_packed; ep.keys_a = ka; ep.keys_b = kb;
-    ep.B = (int)T; ep.N = (int)N; ep.M = (int)M; ep.n_pad = (int)padded_points(N); ep.m_pad = (int)padded_points(M);
+    ep.B = (int)T; ep.N = (int)N; ep.M = (int)M; ep.n_pad = (int)n_pad_sorted; ep.m_pad = (int)padded_points(M);
     ep.row_chunk_pts = kChunk; ep.col_chunk_pts = sp.col_chunk_pts; ep.gscale = 1.0f; ep.g_src = gs; ep.loss = loss;
+    if (sp.col_chunk_pts != 256) return REART_ERR_UNSUPPORTED;       // the sorted copy is built per 256-point chunk
+    ep.src_perm = perm;
     rc = launch_energy_bwd(ep, stream);
     if (rc || !compute_grad) return rc;
     return launch_skin_bwd(cano, W, R, tr, gs, T, N, P, gW, gR, gtr, stream);

@@ -13,11 +13,42 @@
 
 namespace reart {
 
+// Index recovery inside an x-SORTED chunk (skin_fwd_sorted_kernel): only points with |q.x - x| <= sqrt(dmin) can
+// reproduce dmin (d >= fl(dx*dx)), so binary-search that window (with a 1e-5 relative safety margin, the exact test
+// still decides) and take the LOWEST ORIGINAL offset among the exact matches -- the same answer as a linear scan of
+// the unsorted chunk.
+__device__ __forceinline__ int rescan_sorted_chunk(const float* __restrict__ packed_b, const unsigned char* __restrict__ perm_b,
+                                                   unsigned chunk, int chunk_pts, float qx, float qy, float qz, float dmin) {
+    const int base = (int)chunk * chunk_pts;
+    const float* __restrict__ gx = packed_b + (int64_t)(base >> 2) * kGroupFloats;      // x of sorted position k: gx[(k>>2)*12 + (k&3)]
+    const float r = sqrtf(dmin) * 1.00001f + 1e-30f;
+    const float lo = qx - r - fabsf(qx) * 1e-6f, hi = qx + r + fabsf(qx) * 1e-6f;
+    int a = 0, b = chunk_pts;                                                 // first position with x >= lo
+    while (a < b) {
+        const int m = (a + b) >> 1;
+        if (__ldg(gx + (m >> 2) * kGroupFloats + (m & 3)) < lo) a = m + 1; else b = m;
+    }
+    int best = 0x7fffffff;
+    for (int k = a; k < chunk_pts; ++k) {
+        const float* g = gx + (k >> 2) * kGroupFloats + (k & 3);
+        const float x = __ldg(g);
+        if (x > hi) break;
+        const float dx = __fsub_rn(qx, x);
+        if (__fmul_rn(dx, dx) <= dmin && sqdist_scalar(qx, qy, qz, x, __ldg(g + 4), __ldg(g + 8)) == dmin)
+            best = min(best, (int)perm_b[base + k]);
+    }
+    return base + (best == 0x7fffffff ? 0 : best);
+}
+
+// Two launches: the row pass WRITES the direct gradient of every skinned point (plain coalesced stores: no zero
+// fill of g_src, no atomics), the column pass then scatters the reverse-direction terms with float atomics.
+template <bool ROWS>
 __global__ void __launch_bounds__(256) energy_bwd_kernel(const EnergyParams p) {
-    const int64_t nf = (int64_t)p.B * p.N, total = nf + (int64_t)p.B * p.M;
+    const int64_t total = ROWS ? (int64_t)p.B * p.N : (int64_t)p.B * p.M;
     float local = 0.f;
+    const float g2 = 2.0f * p.gscale;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        if (e < nf) {
+        if (ROWS) {
             const int64_t b = e / p.N;
             const u64 key = p.keys_a[e];
             const float dmin = __uint_as_float((unsigned)(key >> 32));
@@ -27,26 +58,29 @@ __global__ void __launch_bounds__(256) energy_bwd_kernel(const EnergyParams p) {
                                  p.row_chunk_pts, p.m_pad, ax, ay, az, dmin);
             if (j >= p.M) j = 0;
             const float* t = p.tgt + (b * p.M + j) * 3;
-            const float g2 = 2.0f * p.gscale;
-            atomicAdd(p.g_src + e * 3 + 0, g2 * (ax - t[0]));
-            atomicAdd(p.g_src + e * 3 + 1, g2 * (ay - t[1]));
-            atomicAdd(p.g_src + e * 3 + 2, g2 * (az - t[2]));
+            p.g_src[e * 3 + 0] = g2 * (ax - t[0]);
+            p.g_src[e * 3 + 1] = g2 * (ay - t[1]);
+            p.g_src[e * 3 + 2] = g2 * (az - t[2]);
             local += dmin;
             if (p.d_fwd) p.d_fwd[e] = dmin;
             if (p.i_fwd) p.i_fwd[e] = j;
         } else {
-            const int64_t f = e - nf;
+            const int64_t f = e;
             const int64_t b = f / p.M;
             const u64 key = p.keys_b[f];
             const float dmin = __uint_as_float((unsigned)(key >> 32));
             const float* a = p.tgt + f * 3;
             const float ax = a[0], ay = a[1], az = a[2];
-            int i = rescan_chunk(p.src_packed + b * (int64_t)p.n_pad * 3, (unsigned)(key & 0xffffffffu),
+            int i;
+            if (p.src_perm)
+                i = rescan_sorted_chunk(p.src_packed + b * (int64_t)p.n_pad * 3, p.src_perm + b * (int64_t)p.n_pad,
+                                        (unsigned)(key & 0xffffffffu), p.col_chunk_pts, ax, ay, az, dmin);
+            else
+                i = rescan_chunk(p.src_packed + b * (int64_t)p.n_pad * 3, (unsigned)(key & 0xffffffffu),
                                  p.col_chunk_pts, p.n_pad, ax, ay, az, dmin);
             if (i >= p.N) i = 0;
             const float* t = p.src + (b * p.N + i) * 3;
             float* go = p.g_src + (b * p.N + i) * 3;
-            const float g2 = 2.0f * p.gscale;
             atomicAdd(go + 0, -g2 * (ax - t[0]));
             atomicAdd(go + 1, -g2 * (ay - t[1]));
             atomicAdd(go + 2, -g2 * (az - t[2]));
@@ -68,12 +102,24 @@ __global__ void __launch_bounds__(256) energy_bwd_kernel(const EnergyParams p) {
     }
 }
 
+// g_src needs NO zero fill (the row pass overwrites it); loss must be zero on entry.
 int launch_energy_bwd(const EnergyParams& p, cudaStream_t stream) {
-    const int64_t total = (int64_t)p.B * (p.N + p.M);
-    if (total <= 0) return kOk;
-    const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
-    energy_bwd_kernel<<<blocks, 256, 0, stream>>>(p);
-    REART_CHECK_LAUNCH();
+    if (p.B <= 0) return kOk;
+    const int64_t rows = (int64_t)p.B * p.N, cols = (int64_t)p.B * p.M;
+    if (rows > 0) {
+        if (p.M <= 0) {
+            if (cudaMemsetAsync(p.g_src, 0, sizeof(float) * (size_t)rows * 3, stream) != cudaSuccess) return kErrLaunch;
+        } else {
+            const int blocks = (int)std::min<int64_t>(ceil_div(rows, 256), 148 * 16);
+            energy_bwd_kernel<true><<<blocks, 256, 0, stream>>>(p);
+            REART_CHECK_LAUNCH();
+        }
+    }
+    if (cols > 0 && p.N > 0) {
+        const int blocks = (int)std::min<int64_t>(ceil_div(cols, 256), 148 * 16);
+        energy_bwd_kernel<false><<<blocks, 256, 0, stream>>>(p);
+        REART_CHECK_LAUNCH();
+    }
     return kOk;
 }
 

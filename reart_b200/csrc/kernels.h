@@ -55,6 +55,9 @@ int launch_chamfer_bidir_bwd(const float* src, const float* tgt, const int64_t* 
 
 int launch_skin_fwd(const float* cano, const float* W, const float* R, const float* tr, int64_t T, int64_t N, int64_t P,
                     float* out, float* out_packed, cudaStream_t stream);
+int launch_skin_fwd_sorted(const float* cano, const float* W, const float* R, const float* tr, int64_t T, int64_t N,
+                           int64_t P, float* out, float* out_packed, unsigned char* perm, int64_t n_pad,
+                           cudaStream_t stream);
 int launch_skin_bwd(const float* cano, const float* W, const float* R, const float* tr, const float* g, int64_t T,
                     int64_t N, int64_t P, float* gW, float* gR, float* gtr, cudaStream_t stream);
 
@@ -87,12 +90,13 @@ struct EnergyParams {
     const float* tgt;             // [B,M,3] observed frames
     const float* src_packed;      // packed copies (re-scan)
     const float* tgt_packed;
+    const unsigned char* src_perm;      // [B,n_pad] or null: src_packed is x-sorted per col_chunk_pts block, perm = original offset
     const unsigned long long* keys_a;   // [B,N] row keys
     const unsigned long long* keys_b;   // [B,M] column keys
     int B, N, M, n_pad, m_pad;
     int row_chunk_pts, col_chunk_pts;
     float gscale;                 // upstream gradient of every per-point distance (1 for torch.sum)
-    float* g_src;                 // [B,N,3], zero on entry
+    float* g_src;                 // [B,N,3], overwritten (the row pass stores, the column pass adds)
     double* loss;                 // [1], zero on entry: sum of all per-point distances
     float* d_fwd; int64_t* i_fwd; // optional [B,N]
     float* d_bwd; int64_t* i_bwd; // optional [B,M]

@@ -82,6 +82,104 @@ int launch_skin_fwd(const float* cano, const float* W, const float* R, const flo
     return kOk;
 }
 
+// ----------------------------------------------------------------------------- forward, x-sorted packed copy
+// Same skinning, but the packed copy is written with every block of kSortBlock (= one column chunk of the symmetric
+// search: the 256 consecutive points one warp owns) SORTED BY X, plus perm[t][k] = original offset of the point now at
+// sorted position k.  The index recovery of the column side (energy.cu) then binary-searches the x window
+// |b.x - a.x| <= sqrt(dmin) instead of testing all 256 candidates (~4 candidates survive on surface clouds).
+// The AoS output keeps the original order -- it is what the search and every consumer read.
+constexpr int kSortBlock = 256;
+
+__device__ __forceinline__ unsigned orderable_bits(float v) {
+    const unsigned u = __float_as_uint(v);
+    return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+
+__global__ void __launch_bounds__(kSortBlock) skin_fwd_sorted_kernel(const float* __restrict__ cano,
+                                                                     const float* __restrict__ W,
+                                                                     const float* __restrict__ R,
+                                                                     const float* __restrict__ tr, int T, int N, int P,
+                                                                     float* __restrict__ out,
+                                                                     float* __restrict__ out_packed,
+                                                                     unsigned char* __restrict__ perm, int n_pad,
+                                                                     int fpb) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    u64* keys = reinterpret_cast<u64*>(sm_raw);                               // [256]
+    float* sx = reinterpret_cast<float*>(keys + kSortBlock);                  // [3][256]
+    float* sm_tf = sx + 3 * kSortBlock;                                       // [fpb][P][12]
+    const int t0 = blockIdx.y * fpb;
+    const int nt = min(fpb, T - t0);
+    for (int e = threadIdx.x; e < nt * P * 12; e += blockDim.x) {
+        const int f = e / (P * 12), rem = e - f * P * 12, p = rem / 12, k = rem - p * 12;
+        const int64_t tp = (int64_t)(t0 + f) * P + p;
+        sm_tf[e] = (k < 9) ? R[tp * 9 + k] : tr[tp * 3 + (k - 9)];
+    }
+    __syncthreads();
+    const int i = threadIdx.x;
+    const int base = blockIdx.x * kSortBlock;
+    const int n = base + i;
+    const bool real = n < N;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (real) { cx = cano[3 * n]; cy = cano[3 * n + 1]; cz = cano[3 * n + 2]; }
+    const float* __restrict__ w = W + (int64_t)(real ? n : 0) * P;
+    for (int f = 0; f < nt; ++f) {
+        float ax = INFINITY, ay = INFINITY, az = INFINITY;                    // padding sorts last
+        if (real) {
+            ax = ay = az = 0.f;
+            const float* tf = sm_tf + f * P * 12;
+            for (int p = 0; p < P; ++p) {
+                const float wp = __ldg(w + p);
+                if (wp != 0.f) {
+                    const float* m = tf + p * 12;
+                    const float vx = cx * m[0] + cy * m[1] + cz * m[2] + m[9];
+                    const float vy = cx * m[3] + cy * m[4] + cz * m[5] + m[10];
+                    const float vz = cx * m[6] + cy * m[7] + cz * m[8] + m[11];
+                    ax += wp * vx; ay += wp * vy; az += wp * vz;
+                }
+            }
+            float* o = out + ((int64_t)(t0 + f) * N + n) * 3;
+            o[0] = ax; o[1] = ay; o[2] = az;
+        }
+        sx[i] = ax; sx[kSortBlock + i] = ay; sx[2 * kSortBlock + i] = az;
+        keys[i] = ((u64)orderable_bits(ax) << 32) | (u64)i;
+        __syncthreads();
+        // bitonic sort of the 256 (x, offset) keys, ascending
+        for (int k = 2; k <= kSortBlock; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const u64 a = keys[i], b = keys[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        const int src = (int)(keys[i] & 0xffu);
+        if (base + i < n_pad) {
+            float* g = out_packed + (int64_t)(t0 + f) * n_pad * 3 + (int64_t)((base + i) >> 2) * kGroupFloats + (i & 3);
+            g[0] = sx[src]; g[4] = sx[kSortBlock + src]; g[8] = sx[2 * kSortBlock + src];
+            perm[(int64_t)(t0 + f) * n_pad + base + i] = (unsigned char)src;
+        }
+        __syncthreads();
+    }
+}
+
+int launch_skin_fwd_sorted(const float* cano, const float* W, const float* R, const float* tr, int64_t T, int64_t N,
+                           int64_t P, float* out, float* out_packed, unsigned char* perm, int64_t n_pad,
+                           cudaStream_t stream) {
+    if (T <= 0 || N <= 0) return kOk;
+    if (P <= 0 || P > 32 || n_pad % kSortBlock != 0 || n_pad < N) return kErrUnsupported;
+    int fpb = kSkinFramesPerBlock;
+    while (fpb > 1 && (n_pad / kSortBlock) * ceil_div(T, fpb) < 2 * 148) fpb /= 2;
+    dim3 grid((unsigned)(n_pad / kSortBlock), (unsigned)ceil_div(T, fpb));
+    const size_t smem = (size_t)kSortBlock * (8 + 12) + (size_t)fpb * P * 12 * sizeof(float);
+    skin_fwd_sorted_kernel<<<grid, kSortBlock, smem, stream>>>(cano, W, R, tr, (int)T, (int)N, (int)P, out, out_packed,
+                                                               perm, (int)n_pad, fpb);
+    REART_CHECK_LAUNCH();
+    return kOk;
+}
+
 // ----------------------------------------------------------------------------- backward
 // g [T,N,3] -> gW [N,P], gR [T,P,9], gtr [T,P,3]
 //   gW[n,p]  = sum_t g[t,n] . (R[t,p] c_n + tr[t,p])                (dense in p: straight-through grads)

@@ -684,3 +684,34 @@ def test_largest_named_size_256k_points_properties():
     assert torch.allclose(((T - nb) ** 2).sum(-1), d_b, rtol=1e-5, atol=1e-12)
     one = knn_points(S[:, :20000].contiguous(), T, K=1)
     assert torch.equal(one.idx[0, :, 0], i_f[0, :20000]) and torch.equal(one.dists[0, :, 0], d_f[0, :20000])
+
+
+def test_fused_energy_gradient_with_exact_ties_and_ragged_sizes():
+    """reart_skinned_chamfer_fwd_bwd called directly (g_skinned exposed): integer-lattice clouds have many exact
+    distance ties, and the gradient depends on WHICH tied neighbour is picked, so this pins the lowest-index rule of
+    the x-sorted column re-scan; N is not a multiple of 256 and N != M."""
+    from reart_b200 import _lib, ops
+    L = _lib.lib()
+    rng = np.random.default_rng(21)
+    for (T, N, M) in [(3, 700, 900), (2, 1000, 333), (1, 257, 4096)]:
+        cano = rng.integers(-3, 4, (N, 3)).astype(np.float32)
+        frames = rng.integers(-3, 4, (T, M, 3)).astype(np.float32)
+        P = 1
+        W = np.ones((N, 1), np.float32)
+        R = np.tile(np.eye(3, dtype=np.float32), (T, 1, 1, 1)); tr = np.zeros((T, 1, 3), np.float32)
+        src = np.tile(cano[None], (T, 1, 1))
+        ref = oracle.chamfer_bidir_fwd_bwd(src, frames)
+        d = dev()
+        cano_t, W_t, R_t, tr_t, fr_t = cu(cano), cu(W), cu(R), cu(tr), cu(frames)
+        packed = ops.pack_cloud(fr_t)
+        skinned = torch.empty(T, N, 3, device=d); loss = torch.zeros(1, dtype=torch.float64, device=d)
+        gW = torch.empty(N, P, device=d); gR = torch.empty(T, P, 3, 3, device=d); gt = torch.empty(T, P, 3, device=d)
+        gs = torch.empty(T, N, 3, device=d)
+        nbytes = L.reart_energy_workspace_bytes(T, N, M); ws = _lib.workspace(nbytes, d)
+        _lib.check(L.reart_skinned_chamfer_fwd_bwd(_lib.ptr(cano_t), _lib.ptr(W_t), _lib.ptr(R_t), _lib.ptr(tr_t),
+                                                   _lib.ptr(fr_t), _lib.ptr(packed), T, N, M, P, _lib.ptr(skinned),
+                                                   _lib.ptr(loss), _lib.ptr(gW), _lib.ptr(gR), _lib.ptr(gt), _lib.ptr(gs),
+                                                   1, _lib.ptr(ws), nbytes, _lib.stream_ptr()), "fused")
+        torch.cuda.synchronize()
+        assert abs(loss.item() - ref["loss"]) <= 1e-6 * max(ref["loss"], 1.0)
+        np.testing.assert_allclose(gs.cpu().numpy(), ref["grad_src"], rtol=0, atol=1e-5)      # integers: exact sums
