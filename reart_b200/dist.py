@@ -157,7 +157,9 @@ def make_small_all_reduce(ctx: DistContext, numel: int, device):
             return OneShotAllReduce(ctx, numel, device)
         except Exception as exc:                                  # symmetric memory not available on this system
             if ctx.is_main:
-                print(f"[reart_b200] one-shot all-reduce unavailable ({type(exc).__name__}: {exc}); using NCCL", flush=True)
+                import sys
+                print(f"[reart_b200] one-shot all-reduce unavailable ({type(exc).__name__}: {exc}); using NCCL",
+                      file=sys.stderr, flush=True)
     return lambda flat: ctx.all_reduce_sum_(flat)
 
 

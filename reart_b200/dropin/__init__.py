@@ -20,9 +20,10 @@ from ..knn_module import KNN
 # The reference's ChamferDistance.forward runs TWO searches back to back, knn_points(src, tgt) then
 # knn_points(tgt, src) (utils/chamfer.py:78-94).  Every distance is symmetric, so the first call evaluates each
 # pair once for both directions (chamfer_sym.cu) and parks the reverse result here; the second call, recognised
-# by the swapped (data_ptr, version, shape) signature, is answered from the cache.  The autograd graph of the
-# first call keeps both tensors alive in between, so a signature cannot be recycled by another tensor.
-_reverse_cache = {"sig": None, "idx": None, "dists": None}
+# by the swapped (data_ptr, version, shape) signature, is answered from the cache.  The entry holds strong
+# references to both tensors, so their storage cannot be recycled for other data while the entry is alive (also
+# under torch.no_grad(), where autograd keeps nothing); any other call drops it.
+_reverse_cache = {"sig": None, "idx": None, "dists": None, "keep": None}
 
 
 def _sig(a, b):
@@ -42,9 +43,9 @@ def _knn_points_idx(p1, p2, lengths1, lengths2, K, version):
     P2 = p2c.shape[1]
     if _reverse_cache["sig"] == _sig(p1c, p2c):
         idx, dists = _reverse_cache["idx"], _reverse_cache["dists"]
-        _reverse_cache.update(sig=None, idx=None, dists=None)
+        _reverse_cache.update(sig=None, idx=None, dists=None, keep=None)
         return idx, dists
-    _reverse_cache.update(sig=None, idx=None, dists=None)
+    _reverse_cache.update(sig=None, idx=None, dists=None, keep=None)
     dists = torch.empty(B, P1, 1, dtype=torch.float32, device=p1.device)
     idx = torch.empty(B, P1, 1, dtype=torch.int64, device=p1.device)
     if P1 >= 256 and P2 >= 256:
@@ -57,7 +58,7 @@ def _knn_points_idx(p1, p2, lengths1, lengths2, K, version):
             _lib.check(L.reart_chamfer_bidir_fwd(_lib.ptr(p1c), _lib.ptr(p2c), B, P1, P2, _lib.ptr(dists), _lib.ptr(idx),
                                                  _lib.ptr(rd), _lib.ptr(ri), _lib.ptr(ws), nbytes, _lib.stream_ptr()),
                        "reart_chamfer_bidir_fwd")
-        _reverse_cache.update(sig=_sig(p2c, p1c), idx=ri, dists=rd)
+        _reverse_cache.update(sig=_sig(p2c, p1c), idx=ri, dists=rd, keep=(p1c, p2c))
         return idx, dists
     nbytes = L.reart_knn1_workspace_bytes(B, P1, P2)
     ws = _lib.workspace(nbytes, p1.device)

@@ -61,7 +61,9 @@ def fk(paths_to_base, reverse_topo, edge_index, axis_list, moment_list, theta_li
     fk[root] = I, fk[c] = fk[parent(c)] @ exp(xi_e(theta[t,e], d[t,e])); one fused kernel forward and one
     backward instead of ~10.5k ATen ops.
     """
-    key = (id(paths_to_base), id(edge_index), tuple(int(p) for p in reverse_topo),
+    # flattening is a few dozen dict look-ups; the device copies are cached by CONTENT (ids of dicts can be recycled)
+    order, parent, edge = flatten_tree(paths_to_base, reverse_topo, edge_index)
+    key = (order.tobytes(), parent.tobytes(), edge.tobytes(),
            None if joint_type_list is None else tuple(joint_type_list), str(theta_list.device))
     tree = _tree_cache.get(key)
     if tree is None:
