@@ -76,7 +76,7 @@ int reart_knn1_fwd(const float* p1, const float* p2, int64_t B, int64_t P1, int6
     KnnParams p = {};
     p.ndir = 1;
     p.B = (int)B;
-    p.dir[0] = KnnDir{p1, packed, keys, dists, idx, (int)P1, (int)P2, (int)padded_points(P2), 0, 0, 0, kChunk};
+    p.dir[0] = KnnDir{p1, packed, keys, dists, idx, (int)P1, (int)P2, (int)padded_points(P2), 0, 0, 0, kChunk, nullptr};
     rc = launch_knn1_search(p, stream);
     if (rc) return rc;
     return launch_knn1_finalize(p, stream);
@@ -84,7 +84,8 @@ int reart_knn1_fwd(const float* p1, const float* p2, int64_t B, int64_t P1, int6
 
 int64_t reart_chamfer_workspace_bytes(int64_t B, int64_t N, int64_t M) {
     if (B < 0 || N < 0 || M < 0) return -1;
-    return packed_bytes(B, N) + packed_bytes(B, M) + keys_bytes(B, N) + keys_bytes(B, M) + kAlign;
+    return align_up(B * round_up(N, 256) * 12) + packed_bytes(B, M) + keys_bytes(B, N) + keys_bytes(B, M) +
+           align_up(B * round_up(N, 256)) + kAlign;
 }
 
 int reart_chamfer_bidir_fwd(const float* src, const float* tgt, int64_t B, int64_t N, int64_t M, float* d_fwd,
@@ -101,13 +102,16 @@ int reart_chamfer_bidir_fwd(const float* src, const float* tgt, int64_t B, int64
         return reart_knn1_fwd(tgt, src, B, M, N, d_bwd, i_bwd, workspace, workspace_bytes, stream_);
     }
     if (!src || !tgt || !d_fwd || !i_fwd || !d_bwd || !i_bwd) return REART_ERR_INVALID_ARG;
+    // src's packed copy is only read by the column-side index recovery: x-sorted per 256-point chunk
+    const int64_t n_pad_sorted = round_up(N, 256);
     Carver ws(workspace, workspace_bytes);
-    float* psrc = ws.take<float>(B * packed_floats_per_batch(N));
+    float* psrc = ws.take<float>(B * n_pad_sorted * 3);
     float* ptgt = ws.take<float>(B * packed_floats_per_batch(M));
     u64* kf = ws.take<u64>(B * N);
     u64* kb = ws.take<u64>(B * M);
+    unsigned char* perm = ws.take<unsigned char>(B * n_pad_sorted);
     if (!ws.ok) return REART_ERR_WORKSPACE;
-    int rc = launch_pack_cloud(src, psrc, B, N, stream);
+    int rc = launch_pack_cloud_sorted(src, psrc, perm, B, N, n_pad_sorted, stream);
     if (rc) return rc;
     rc = launch_pack_cloud(tgt, ptgt, B, M, stream);
     if (rc) return rc;
@@ -117,11 +121,12 @@ int reart_chamfer_bidir_fwd(const float* src, const float* tgt, int64_t B, int64
     sp.B = (int)B; sp.na = (int)N; sp.nb = (int)M; sp.nb_pad = (int)padded_points(M);
     rc = launch_chamfer_sym(sp, stream);
     if (rc) return rc;
+    if (sp.col_chunk_pts != 256) return REART_ERR_UNSUPPORTED;
     KnnParams p = {};
     p.ndir = 2;
     p.B = (int)B;
-    p.dir[0] = KnnDir{src, ptgt, kf, d_fwd, i_fwd, (int)N, (int)M, (int)padded_points(M), 0, 0, 0, kChunk};
-    p.dir[1] = KnnDir{tgt, psrc, kb, d_bwd, i_bwd, (int)M, (int)N, (int)padded_points(N), 0, 0, 0, sp.col_chunk_pts};
+    p.dir[0] = KnnDir{src, ptgt, kf, d_fwd, i_fwd, (int)N, (int)M, (int)padded_points(M), 0, 0, 0, kChunk, nullptr};
+    p.dir[1] = KnnDir{tgt, psrc, kb, d_bwd, i_bwd, (int)M, (int)N, (int)n_pad_sorted, 0, 0, 0, sp.col_chunk_pts, perm};
     return launch_knn1_finalize(p, stream);
 }
 

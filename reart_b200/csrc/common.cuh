@@ -142,4 +142,31 @@ __device__ __forceinline__ int rescan_chunk(const float* __restrict__ tpacked_b,
     return start;   // unreachable for finite inputs (the minimum was produced by this very arithmetic)
 }
 
+// Index recovery inside an x-SORTED chunk (skin_fwd_sorted_kernel): only points with |q.x - x| <= sqrt(dmin) can
+// reproduce dmin (d >= fl(dx*dx)), so binary-search that window (with a 1e-5 relative safety margin, the exact test
+// still decides) and take the LOWEST ORIGINAL offset among the exact matches -- the same answer as a linear scan of
+// the unsorted chunk.
+__device__ __forceinline__ int rescan_sorted_chunk(const float* __restrict__ packed_b, const unsigned char* __restrict__ perm_b,
+                                                   unsigned chunk, int chunk_pts, float qx, float qy, float qz, float dmin) {
+    const int base = (int)chunk * chunk_pts;
+    const float* __restrict__ gx = packed_b + (int64_t)(base >> 2) * kGroupFloats;      // x of sorted position k: gx[(k>>2)*12 + (k&3)]
+    const float r = sqrtf(dmin) * 1.00001f + 1e-30f;
+    const float lo = qx - r - fabsf(qx) * 1e-6f, hi = qx + r + fabsf(qx) * 1e-6f;
+    int a = 0, b = chunk_pts;                                                 // first position with x >= lo
+    while (a < b) {
+        const int m = (a + b) >> 1;
+        if (__ldg(gx + (m >> 2) * kGroupFloats + (m & 3)) < lo) a = m + 1; else b = m;
+    }
+    int best = 0x7fffffff;
+    for (int k = a; k < chunk_pts; ++k) {
+        const float* g = gx + (k >> 2) * kGroupFloats + (k & 3);
+        const float x = __ldg(g);
+        if (x > hi) break;
+        const float dx = __fsub_rn(qx, x);
+        if (__fmul_rn(dx, dx) <= dmin && sqdist_scalar(qx, qy, qz, x, __ldg(g + 4), __ldg(g + 8)) == dmin)
+            best = min(best, (int)perm_b[base + k]);
+    }
+    return base + (best == 0x7fffffff ? 0 : best);
+}
+
 }  // namespace reart

@@ -19,6 +19,7 @@ struct KnnDir {
     int splits;                   // filled by the launcher
     int keys_preset;              // 1: caller already set keys to 0xff.. (fused pipelines)
     int chunk_pts;                // targets per arg-min chunk recorded in the key (finalize re-scan span)
+    const unsigned char* perm;    // null, or [B,nt_pad]: tpacked is x-sorted per chunk_pts block (perm = original offset)
 };
 
 struct KnnParams {
@@ -42,6 +43,8 @@ struct SymParams {
 };
 
 int launch_pack_cloud(const float* pts, float* packed, int64_t B, int64_t P, cudaStream_t stream);
+int launch_pack_cloud_sorted(const float* pts, float* packed, unsigned char* perm, int64_t B, int64_t P, int64_t n_pad,
+                             cudaStream_t stream);
 int launch_knn1_search(KnnParams& p, cudaStream_t stream);
 int launch_knn1_finalize(const KnnParams& p, cudaStream_t stream);
 int launch_chamfer_sym(SymParams& p, cudaStream_t stream);

@@ -63,6 +63,46 @@ int launch_pack_cloud(const float* pts, float* packed, int64_t B, int64_t P, cud
     return kOk;
 }
 
+// pts [B,P,3] -> packed [B, n_pad/4, 12] with every block of 256 points sorted by x (+INF padding last) and
+// perm [B,n_pad] = original offset inside the block of the point now at each sorted position (see skin.cu
+// skin_fwd_sorted_kernel, which does the same for the skinned cloud).  n_pad is a multiple of 256.
+__global__ void __launch_bounds__(256) pack_cloud_sorted_kernel(const float* __restrict__ pts, float* __restrict__ packed,
+                                                                unsigned char* __restrict__ perm, int P, int n_pad) {
+    __shared__ u64 keys[256];
+    __shared__ float sx[3 * 256];
+    const int b = blockIdx.y, i = threadIdx.x, base = blockIdx.x * 256, n = base + i;
+    float x = INFINITY, y = INFINITY, z = INFINITY;
+    if (n < P) { const float* s = pts + ((int64_t)b * P + n) * 3; x = s[0]; y = s[1]; z = s[2]; }
+    sx[i] = x; sx[256 + i] = y; sx[512 + i] = z;
+    const unsigned u = __float_as_uint(x);
+    keys[i] = ((u64)(u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u)) << 32) | (u64)i;
+    __syncthreads();
+    for (int k = 2; k <= 256; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int ixj = i ^ j;
+            if (ixj > i) {
+                const u64 a = keys[i], c = keys[ixj];
+                if ((a > c) == ((i & k) == 0)) { keys[i] = c; keys[ixj] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    const int src = (int)(keys[i] & 0xffu);
+    float* g = packed + (int64_t)b * n_pad * 3 + (int64_t)(n >> 2) * kGroupFloats + (i & 3);
+    g[0] = sx[src]; g[4] = sx[256 + src]; g[8] = sx[512 + src];
+    perm[(int64_t)b * n_pad + n] = (unsigned char)src;
+}
+
+int launch_pack_cloud_sorted(const float* pts, float* packed, unsigned char* perm, int64_t B, int64_t P, int64_t n_pad,
+                             cudaStream_t stream) {
+    if (B <= 0) return kOk;
+    if (n_pad % 256 != 0 || n_pad < P || B > 65535) return kErrUnsupported;
+    dim3 grid((unsigned)(n_pad / 256), (unsigned)B);
+    pack_cloud_sorted_kernel<<<grid, 256, 0, stream>>>(pts, packed, perm, (int)P, (int)n_pad);
+    REART_CHECK_LAUNCH();
+    return kOk;
+}
+
 // ----------------------------------------------------------------------------- main search
 template <int R, int THREADS>
 __global__ void __launch_bounds__(THREADS, (R <= 8 && THREADS <= 256) ? 2 : 1) knn1_main_kernel(const KnnParams p) {
@@ -183,7 +223,9 @@ __global__ void knn1_finalize_kernel(const KnnParams p, int dir_only) {
             const float dmin = __uint_as_float((unsigned)(key >> 32));
             const unsigned chunk = (unsigned)(key & 0xffffffffu);
             const float* qp = D.q + e * 3;
-            int j = rescan_chunk(D.tpacked + b * (int64_t)D.nt_pad * 3, chunk, D.chunk_pts, D.nt_pad, qp[0], qp[1], qp[2], dmin);
+            int j = D.perm ? rescan_sorted_chunk(D.tpacked + b * (int64_t)D.nt_pad * 3, D.perm + b * (int64_t)D.nt_pad, chunk,
+                                                 D.chunk_pts, qp[0], qp[1], qp[2], dmin)
+                           : rescan_chunk(D.tpacked + b * (int64_t)D.nt_pad * 3, chunk, D.chunk_pts, D.nt_pad, qp[0], qp[1], qp[2], dmin);
             if (j >= D.nt) j = 0;
             if (D.out_dists) D.out_dists[e] = dmin;
             if (D.out_idx) D.out_idx[e] = (int64_t)j;
