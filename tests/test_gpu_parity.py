@@ -715,3 +715,38 @@ def test_fused_energy_gradient_with_exact_ties_and_ragged_sizes():
         torch.cuda.synchronize()
         assert abs(loss.item() - ref["loss"]) <= 1e-6 * max(ref["loss"], 1.0)
         np.testing.assert_allclose(gs.cpu().numpy(), ref["grad_src"], rtol=0, atol=1e-5)      # integers: exact sums
+
+
+def _oneshot_worker(rank, world, port, out_dir):
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from reart_b200.dist import DistContext, OneShotAllReduce
+    ctx = DistContext.from_env(backend="nccl")
+    d = torch.device("cuda", rank)
+    ar = OneShotAllReduce(ctx, 2433, d)
+    g = torch.Generator(device=d).manual_seed(50 + rank)
+    worst = 0.0
+    for _ in range(5):
+        x = torch.randn(2433, device=d, generator=g)
+        ref = x.clone(); dist.all_reduce(ref)
+        y = x.clone(); ar(y); torch.cuda.synchronize()
+        worst = max(worst, float((y - ref).abs().max()))
+    np.save(os.path.join(out_dir, f"r{rank}.npy"), np.array([worst]))
+    np.save(os.path.join(out_dir, f"y{rank}.npy"), y.cpu().numpy())
+    dist.barrier()
+    os._exit(0)
+
+
+@pytest.mark.timeout(180)
+def test_oneshot_allreduce_matches_nccl_on_two_gpus(tmp_path):
+    """csrc/allreduce.cu over NVLink peer memory vs NCCL (runs only where >= 2 GPUs are visible)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_oneshot_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert float(np.load(tmp_path / "r0.npy")[0]) < 1e-5 and float(np.load(tmp_path / "r1.npy")[0]) < 1e-5
+    assert np.array_equal(np.load(tmp_path / "y0.npy"), np.load(tmp_path / "y1.npy"))      # identical bits on both ranks
