@@ -114,48 +114,106 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """SM clock / power / throttle reasons DURING the timed region.  The timed region of the default run is < 0.1 s,
+    shorter than nvidia-smi's start-up, so the primary source is an in-process NVML thread (the library nvidia-smi
+    itself reads) polling every ~4 ms between begin() and end(); an `nvidia-smi -lms 20` subprocess started early is
+    the fallback, filtered to the same wall-clock window."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.path = tempfile.NamedTemporaryFile(suffix=".csv", delete=False).name
-        self.proc = None
+    def __init__(self, gpu_index: int, uuid: str | None = None):
+        import threading
+        self.samples = []                                  # (wall time, sm MHz, max MHz, watts, reasons tuple)
+        self.t0 = self.t1 = None
+        self._stop = threading.Event()
+        self._thread = None
+        self.smi_path, self.smi = None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(gpu_index)], stdout=open(self.path, "w"),
-                                         stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        try:
+                            r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        except Exception:
+                            r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.samples.append((time.time(), sm, mx, pw, tuple(k for k, b in bits.items() if r & b)))
+                    except Exception:
+                        pass
+                    time.sleep(0.004)
+
+            self._thread = threading.Thread(target=poll, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc.kill()
-        sm, mx, power, reasons = [], [], [], set()
+            self._thread = None
+        try:
+            self.smi_path = tempfile.NamedTemporaryFile(suffix=".csv", delete=False).name
+            self.smi = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                         "-lms", "20", "-i", str(gpu_index)], stdout=open(self.smi_path, "w"),
+                                        stderr=subprocess.DEVNULL)
+        except Exception:
+            self.smi = None
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
+    def _smi_samples(self):
+        import datetime
+        out = []
+        if self.smi is None:
+            return out
+        self.smi.terminate()
+        try:
+            self.smi.wait(timeout=5)
+        except Exception:
+            self.smi.kill()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 9:
+        for line in open(self.smi_path):
+            parts = [q.strip() for q in line.split(",")]
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[1])); mx.append(float(parts[2])); power.append(float(parts[3]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                out.append((ts, float(parts[1]), float(parts[2]), float(parts[3]),
+                            tuple(n for n, v in zip(names, parts[4:8]) if v.lower().startswith("active"))))
             except ValueError:
                 continue
-            for name, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.path)
-        if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
-                       power_w_max=max(power))
+        os.unlink(self.smi_path)
+        return out
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
+        source = "nvml"
+        sel = [q for q in self.samples if self.t0 is not None and self.t0 <= q[0] <= (self.t1 or time.time())]
+        smi = self._smi_samples()
+        if len(sel) < 3:
+            sel = [q for q in smi if self.t0 is not None and self.t0 - 0.02 <= q[0] <= (self.t1 or time.time()) + 0.02]
+            source = "nvidia-smi"
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(sel), "source": source}
+        if sel:
+            sm = sorted(q[1] for q in sel)
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(q[2] for q in sel),
+                       reasons=sorted({r for q in sel for r in q[4]}), power_w_max=max(q[3] for q in sel))
         return out
 
 
@@ -201,6 +259,7 @@ def main():
     pairs_per_step = 2.0 * T_total * N * N
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(ctx.local_rank, str(torch.cuda.get_device_properties(dev).uuid)) if ctx.is_main else None
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
     for i in range(W):
@@ -208,9 +267,10 @@ def main():
     torch.cuda.synchronize()
 
     # ---- timed region: K steps, each bracketed by its own events, L2 flushed in between (untimed)
-    sampler = ClockSampler(ctx.local_rank) if ctx.is_main else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     ctx.barrier(); torch.cuda.synchronize()
+    if sampler:
+        sampler.begin()
     t_wall0 = time.perf_counter()
     for i in range(K):
         flush.fill_(i & 0xff)
@@ -220,6 +280,8 @@ def main():
         ev[i][1].record()
     torch.cuda.synchronize(); ctx.barrier()
     wall_s = time.perf_counter() - t_wall0
+    if sampler:
+        sampler.end()
     clocks = sampler.stop() if sampler else None
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
