@@ -34,15 +34,11 @@ class SegHead(nn.Module):
         return self.model(x)
 
     def logits(self, points: torch.Tensor) -> torch.Tensor:
-        """[N,3] -> [N,P].  A k=1 Conv1d IS a per-point matmul: on CUDA the two layers run as one fused fp32 kernel
-        (forward and backward, csrc/segmlp.cu) on the conv parameters themselves -- identical state_dict; it also
-        avoids cuDNN's default TF32, so the logits match the reference's CPU arithmetic to fp32 round-off.
-        On CPU tensors the same math is two torch GEMMs (plain torch, no kernel of ours involved)."""
+        """[N,3] -> [N,P].  A k=1 Conv1d IS a per-point matmul: the two layers run as one fused fp32 kernel each way
+        (csrc/segmlp.cu) on the conv parameters themselves -- identical state_dict; it also avoids cuDNN's default
+        TF32, so the logits match the reference's CPU arithmetic to fp32 round-off.  CUDA tensors only (no fallback)."""
         w0, b0, w2 = self.model[0].weight[:, :, 0], self.model[0].bias, self.model[2].weight[:, :, 0]
-        if points.is_cuda:
-            return ops.seg_mlp(points, w0, b0, w2, getattr(self, "grad_sink", None))
-        h = torch.relu(torch.addmm(b0, points, w0.t()))
-        return h @ w2.t()
+        return ops.seg_mlp(points, w0, b0, w2, getattr(self, "grad_sink", None))
 
 
 def _assemble(R: torch.Tensor, tr: torch.Tensor) -> torch.Tensor:
@@ -93,9 +89,7 @@ class BaseModel(nn.Module):
     def weights(self, cano_pc, tau=1.0):
         """Straight-through gumbel-softmax assignment (networks/model.py:42-44); draws RNG every call."""
         seg = self.seg_logits(cano_pc)
-        if seg.is_cuda:
-            return seg, ops.gumbel_softmax_st(seg, tau)
-        return seg, F.gumbel_softmax(seg, tau=tau, hard=True)
+        return seg, ops.gumbel_softmax_st(seg, tau)
 
     def forward(self, cano_pc, **kwargs):
         seg, weight = self.weights(cano_pc, tau=kwargs.get("tau", 1.0))
