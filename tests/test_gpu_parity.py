@@ -750,3 +750,29 @@ def test_oneshot_allreduce_matches_nccl_on_two_gpus(tmp_path):
     mp.spawn(_oneshot_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert float(np.load(tmp_path / "r0.npy")[0]) < 1e-5 and float(np.load(tmp_path / "r1.npy")[0]) < 1e-5
     assert np.array_equal(np.load(tmp_path / "y0.npy"), np.load(tmp_path / "y1.npy"))      # identical bits on both ranks
+
+
+def test_register_blocked_topk_and_blend_path_vs_oracle():
+    """m >= 2048 queries take the tiled packed-math k-NN kernel: same indices/distances as the oracle, ragged
+    reference sets, ties (duplicated references) keep the lowest index."""
+    from reart_b200 import ops
+    from reart_b200.flow_utils import FlowReference, blend_anchor_motion_batched
+    rng = np.random.default_rng(33)
+    q = (rng.standard_normal((2, 3000, 3)) * 0.3).astype(np.float32)
+    ref = (rng.standard_normal((2, 2501, 3)) * 0.3).astype(np.float32)
+    ref[:, 1200:1210] = ref[:, 100:110]                               # exact duplicates => ties
+    for k in (1, 3, 4):
+        d, i = ops.knn(cu(ref), cu(q), k)
+        for b in range(2):
+            d_o, i_o = oracle.knn(ref[b], q[b], k)
+            assert np.array_equal(i[b].cpu().numpy(), i_o)
+            np.testing.assert_allclose(d[b].cpu().numpy(), d_o, rtol=1e-6)
+    sizes = [1800, 2501, 37]
+    refs = [cu(ref[0, :n]) for n in sizes]
+    flows = [cu((rng.standard_normal((n, 3)) * 0.05).astype(np.float32)) for n in sizes]
+    queries = cu((rng.standard_normal((3, 2600, 3)) * 0.3).astype(np.float32))
+    B, M = blend_anchor_motion_batched(queries, FlowReference(refs, flows))
+    for t in range(3):
+        b_o, m_o = oracle.blend_anchor_motion(queries[t].cpu().numpy(), refs[t].cpu().numpy(), flows[t].cpu().numpy())
+        np.testing.assert_allclose(B[t].cpu().numpy(), b_o, rtol=1e-4, atol=1e-7)
+        assert (M[t].cpu().numpy() == m_o).mean() > 0.999
