@@ -163,6 +163,81 @@ def make_small_all_reduce(ctx: DistContext, numel: int, device):
     return lambda flat: ctx.all_reduce_sum_(flat)
 
 
+def flow_pairs_for_rank(T: int, cano_idx: int, lo: int, hi: int):
+    """Which consecutive pairs of the COMPLETE sequence (canonical frame inserted at cano_idx, run_robot.py:204-207)
+    a rank owning skinned frames [lo, hi) evaluates, and where each side comes from.
+
+    Returns (p0, p1, a_src, b_src): pairs p in [p0, p1) and per pair the source of complete[p] / complete[p+1] as
+    ("local", i) (i-th local frame), ("cano",) or ("halo",) (the previous rank's last frame).  A pair belongs to
+    the owner of its SECOND frame, or of its first one when the second is the canonical frame; every pair is
+    owned exactly once and only a previous-rank halo is ever needed."""
+    def src(k):
+        if k == cano_idx:
+            return ("cano",)
+        g = k if k < cano_idx else k - 1
+        if lo <= g < hi:
+            return ("local", g - lo)
+        if g == lo - 1:
+            return ("halo",)
+        return None
+
+    def frame(k):
+        return None if k == cano_idx else (k if k < cano_idx else k - 1)
+
+    pairs, a_src, b_src = [], [], []
+    for p in range(T):
+        gB, gA = frame(p + 1), frame(p)
+        owner_frame = gB if gB is not None else gA
+        if owner_frame is not None and lo <= owner_frame < hi:
+            pairs.append(p); a_src.append(src(p)); b_src.append(src(p + 1))
+    if not pairs:
+        return 0, 0, [], []
+    assert pairs == list(range(pairs[0], pairs[-1] + 1)) and all(x is not None for x in a_src + b_src)
+    return pairs[0], pairs[-1] + 1, a_src, b_src
+
+
+class _HaloPrev(torch.autograd.Function):
+    """Forward: every rank sends its last local skinned frame to the next rank and receives the previous rank's
+    (rank 0 receives nothing and gets zeros).  Backward: the gradient of the received frame travels back.
+    One frame [N,3] per shard boundary per direction -- the only data-path message of the flow loss."""
+
+    @staticmethod
+    def forward(ctx, x_last, rank, world):
+        ctx.rank, ctx.world = rank, world
+        recv = torch.zeros_like(x_last)
+        ops_ = []
+        send = x_last.detach().contiguous()
+        if rank < world - 1:
+            ops_.append(dist.P2POp(dist.isend, send, rank + 1))
+        if rank > 0:
+            ops_.append(dist.P2POp(dist.irecv, recv, rank - 1))
+        if ops_:
+            for req in dist.batch_isend_irecv(ops_):
+                req.wait()
+        return recv
+
+    @staticmethod
+    def backward(ctx, g_recv):
+        rank, world = ctx.rank, ctx.world
+        g_last = torch.zeros_like(g_recv)
+        ops_ = []
+        g_send = g_recv.contiguous()
+        if rank > 0:
+            ops_.append(dist.P2POp(dist.isend, g_send, rank - 1))
+        if rank < world - 1:
+            ops_.append(dist.P2POp(dist.irecv, g_last, rank + 1))
+        if ops_:
+            for req in dist.batch_isend_irecv(ops_):
+                req.wait()
+        return g_last, None, None
+
+
+def halo_from_previous_rank(x_last: torch.Tensor, ctx: DistContext) -> torch.Tensor:
+    if ctx.world_size <= 1:
+        return torch.zeros_like(x_last)
+    return _HaloPrev.apply(x_last, ctx.rank, ctx.world_size)
+
+
 def select_best_candidate(ctx: DistContext, energy: float, device=None) -> Tuple[int, List[float]]:
     """cano_idx candidate fits are independent runs, one per rank (README.md:60; energy = total_err,
     run_robot.py:314): gather the scalars and return (rank of the lowest energy, all energies)."""

@@ -119,11 +119,12 @@ class RelaxationEngine(_EngineBase):
         run_robot.py:194-213 (single rank only: consecutive frames couple across shard boundaries)."""
         super().__init__(ctx, use_graph)
         self.flow_ref, self.cano_idx, self.lambda_flow, self.robust_flow = flow_ref, cano_idx, lambda_flow, robust_flow
-        if flow_ref is not None and self.ctx.world_size > 1:
-            raise NotImplementedError("the flow loss couples frames t and t+1; it is supported on one rank only")
+        # the flow loss couples consecutive frames: under frame sharding each rank evaluates the pairs whose second
+        # frame it owns and receives ONE skinned frame (the previous rank's last) per iteration (dist.py)
         dev = cano.device
         lo, hi = self.ctx.frames(frames.shape[0])
         self.frame_range = (lo, hi)
+        self.total_frames = int(frames.shape[0])
         self.cano = cano.float().contiguous()
         self.frames = frames[lo:hi].float().contiguous()          # local shard of the observed frames
         self.frames_packed = ops.pack_cloud(self.frames)          # constant over the optimisation: packed once
@@ -156,11 +157,32 @@ class RelaxationEngine(_EngineBase):
         from .flow_utils import blend_anchor_motion_batched
         from .loss import flow_loss
         c = self.cano_idx
-        complete = torch.cat((pc_trans_list[:c], self.cano[None], pc_trans_list[c:]), dim=0)
+        if self.ctx.world_size == 1:
+            complete = torch.cat((pc_trans_list[:c], self.cano[None], pc_trans_list[c:]), dim=0)
+            with torch.no_grad():
+                target_flow, mask = blend_anchor_motion_batched(complete[:-1].detach().contiguous(), self.flow_ref)
+            pred_flow = complete[1:] - complete[:-1]
+            return flow_loss(target_flow, pred_flow, flow_mask_list=mask, robust=self.robust_flow)
+        # frame-sharded: own pairs [p0, p1), sides taken from local frames, the canonical cloud or the halo frame
+        from .dist import flow_pairs_for_rank, halo_from_previous_rank
+        lo, hi = self.frame_range
+        halo = halo_from_previous_rank(pc_trans_list[-1], self.ctx)          # every rank takes part, even with no pairs
+        # the halo's backward is a matched send/recv: tie it into every rank's loss (weight 0) so it always runs,
+        # also on ranks that do not consume their halo (rank 0) or own no pair
+        anchor = halo.sum() * 0.0
+        p0, p1, a_src, b_src = flow_pairs_for_rank(self.total_frames, c, lo, hi)
+        if p1 <= p0:
+            return anchor
+
+        def pick(src):
+            return self.cano if src[0] == "cano" else (halo if src[0] == "halo" else pc_trans_list[src[1]])
+
+        A = torch.stack([pick(x) for x in a_src])
+        Bm = torch.stack([pick(x) for x in b_src])
         with torch.no_grad():
-            target_flow, mask = blend_anchor_motion_batched(complete[:-1].detach().contiguous(), self.flow_ref)
-        pred_flow = complete[1:] - complete[:-1]
-        return flow_loss(target_flow, pred_flow, flow_mask_list=mask, robust=self.robust_flow)
+            sub = self.flow_ref.slice(p0, p1)
+            target_flow, mask = blend_anchor_motion_batched(A.detach().contiguous(), sub)
+        return flow_loss(target_flow, Bm - A, flow_mask_list=mask, robust=self.robust_flow) + anchor
 
 
 class KinematicEngine(_EngineBase):

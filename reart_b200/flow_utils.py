@@ -41,6 +41,14 @@ class FlowReference:
         self.offsets = torch.tensor(off, dtype=torch.int64, device=dev)
         self.T = len(lens)
 
+    def slice(self, p0: int, p1: int) -> "FlowReference":
+        """The pairs [p0, p1) as a view (shared storage; offsets stay relative to the concatenated arrays)."""
+        sub = object.__new__(FlowReference)
+        sub.ref_cat, sub.flow_cat = self.ref_cat, self.flow_cat
+        sub.offsets = self.offsets[p0:p1 + 1].contiguous()
+        sub.T = p1 - p0
+        return sub
+
 
 def blend_anchor_motion_batched(query_list: torch.Tensor, ref: FlowReference):
     """All T frame pairs of run_robot.py:199-202 in one launch: query [T,m,3] -> (flow [T,m,3], mask [T,m])."""

@@ -83,3 +83,52 @@ def test_two_rank_frame_sharding_reproduces_single_rank_energy(tmp_path):
     e = r0["energies"]
     assert int(r0["best"]) == int(r1["best"]) == int(np.argmin(e))
     np.testing.assert_allclose(e, [float(r0["local_loss"]), float(r1["local_loss"])])
+
+
+def test_flow_pairs_partition_every_pair_exactly_once():
+    from reart_b200.dist import flow_pairs_for_rank, shard_bounds
+    for T in (1, 5, 8, 9, 64):
+        for G in (1, 2, 3, 8):
+            for c in sorted({0, 1, T // 2, T - 1, T}):
+                owned = []
+                for r in range(G):
+                    lo, hi = shard_bounds(T, G, r)
+                    p0, p1, a, b = flow_pairs_for_rank(T, c, lo, hi)
+                    owned += list(range(p0, p1))
+                    for x in a + b:
+                        assert x[0] in ("local", "cano", "halo")
+                        if x[0] == "local":
+                            assert 0 <= x[1] < hi - lo
+                        if x[0] == "halo":
+                            assert lo > 0
+                    assert all(x != ("halo",) for x in b)           # only first frames of a pair come from the halo
+                assert sorted(owned) == list(range(T)), (T, G, c, owned)
+
+
+def _halo_worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from reart_b200.dist import DistContext, halo_from_previous_rank
+    ctx = DistContext.from_env(backend="gloo")
+    x = (torch.arange(6, dtype=torch.float32).reshape(2, 3) + 10 * rank).requires_grad_(True)
+    h = halo_from_previous_rank(x, ctx)
+    (h * (rank + 1.0)).sum().backward()
+    np.savez(os.path.join(out_dir, f"halo{rank}.npz"), h=h.detach().numpy(), g=x.grad.numpy())
+    ctx.barrier()
+    ctx.destroy()
+
+
+@pytest.mark.timeout(300)
+def test_halo_exchange_forward_and_backward_over_gloo(tmp_path):
+    world = 3
+    mp.spawn(_halo_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    base = np.arange(6, dtype=np.float32).reshape(2, 3)
+    for r in range(world):
+        d = np.load(tmp_path / f"halo{r}.npz")
+        want_h = base + 10 * (r - 1) if r > 0 else np.zeros_like(base)
+        assert np.array_equal(d["h"], want_h)
+        # d/dx_last of rank r = weight used by rank r+1 on its received copy (r+2), zero for the last rank
+        want_g = np.full_like(base, r + 2.0) if r < world - 1 else np.zeros_like(base)
+        assert np.array_equal(d["g"], want_g)
