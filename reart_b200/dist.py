@@ -111,7 +111,10 @@ class GradBucket:
 
     def all_reduce(self, ctx: DistContext) -> None:
         self.pack()
-        ctx.all_reduce_sum_(self.flat)
+        if ctx.world_size > 1:
+            if getattr(self, "_reducer", None) is None:
+                self._reducer = make_small_all_reduce(ctx, self.flat.numel(), self.flat.device)
+            self._reducer(self.flat)
         self.unpack()
 
 
