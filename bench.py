@@ -374,10 +374,10 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                         "what": "pinned host cano+frames -> H2D -> pack -> full iteration -> loss D2H, per step"},
-                # our kernels per step and rank: segmlp fwd, gumbel fwd, rot6d fwd, skin fwd, chamfer_sym, energy bwd,
-                # skin bwd (w + pose), rot6d bwd, gumbel bwd, segmlp bwd
-                # (kinematic model: fk fwd, skin fwd, chamfer_sym, energy bwd, skin bwd (w + pose), fk bwd)
-                "gpu_launches": (7 if args.workload == "cfg4" else 11) * K, "cuda_graph": not args.no_graph,
+                # our kernels per step and rank: segmlp fwd, gumbel fwd, rot6d fwd, skin fwd, chamfer_sym, energy rows +
+                # columns, skin bwd (w + pose), rot6d bwd, gumbel bwd, segmlp bwd
+                # (kinematic model: fk fwd, skin fwd, chamfer_sym, energy rows + columns, skin bwd (w + pose), fk bwd)
+                "gpu_launches": (8 if args.workload == "cfg4" else 12) * K, "cuda_graph": not args.no_graph,
                 "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     # teardown: captured graphs reference the NCCL communicator, release them first; with more than one rank

@@ -30,8 +30,8 @@ constexpr int kSymWarps = kSymThreads / 32;
 
 // R  = A points per thread (registers); S = column sub-chunks per warp: the lane's R distances to a target are
 // folded in S groups of R/S, each group goes through its own REDUX, so a column chunk is 32*R/S consecutive A
-// points.  In-lane folds + REDUX count R per target for every S, but a REDUX costs ~4 issue slots on B200 (measured),
-// so S=1 is the production setting; S is also bounded by shared memory
+// points.  In-lane folds + REDUX count R per target for every S, yet larger S measured slower on B200 (more
+// predicated stores, a wider per-tile fold, smaller tiles), so S=1 is the production setting; S is also bounded by shared memory
 // (2 buffers x 8 warps x S x tile points x 4 B), which is why the tile shrinks as S grows.
 template <int R, int S>
 struct SymCfg {
@@ -249,8 +249,8 @@ static int launch_sym_rs(SymParams& p, cudaStream_t stream) {
 
 int launch_chamfer_sym(SymParams& p, cudaStream_t stream) {
     // Measured on B200 (profiles/r01_sym_variants.log, T=64 x 16k): S=1 3.70 ms, S=2 3.87, S=4 4.17, S=8 4.45 --
-    // a REDUX costs ~4 issue slots, so one REDUX per target (S=1, 256-point column chunks) is the fastest search
-    // even after paying for the wider index-recovery re-scan.
+    // one REDUX per target (S=1, 256-point column chunks) is the fastest search even after paying for the wider
+    // index recovery (which the x-sorted packed copy makes cheap, skin.cu / energy.cu).
     switch (p.variant % 16) {
         case 2: return launch_sym_rs<8, 2>(p, stream);
         case 4: return launch_sym_rs<8, 4>(p, stream);
