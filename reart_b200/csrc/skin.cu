@@ -170,9 +170,8 @@ int launch_skin_fwd_sorted(const float* cano, const float* W, const float* R, co
                            cudaStream_t stream) {
     if (T <= 0 || N <= 0) return kOk;
     if (P <= 0 || P > 32 || n_pad % kSortBlock != 0 || n_pad < N) return kErrUnsupported;
-    // each frame costs a 36-step block-wide sort: the per-block chain is latency bound, so prefer many short blocks
     int fpb = kSkinFramesPerBlock;
-    while (fpb > 1 && (n_pad / kSortBlock) * ceil_div(T, fpb) < 16 * 148) fpb /= 2;
+    while (fpb > 1 && (n_pad / kSortBlock) * ceil_div(T, fpb) < 2 * 148) fpb /= 2;
     dim3 grid((unsigned)(n_pad / kSortBlock), (unsigned)ceil_div(T, fpb));
     const size_t smem = (size_t)kSortBlock * (8 + 12) + (size_t)fpb * P * 12 * sizeof(float);
     skin_fwd_sorted_kernel<<<grid, kSortBlock, smem, stream>>>(cano, W, R, tr, (int)T, (int)N, (int)P, out, out_packed,
