@@ -186,18 +186,29 @@ def knn_points(
     return_nn: bool = False,
     return_sorted: bool = True,
 ):
-    """Same signature as utils/chamfer.py:212-286; K == 1 and D == 3 only (the hot path)."""
+    """Same signature as utils/chamfer.py:212-286; D == 3, full lengths; K == 1 is the hot path (fused kernels),
+    2 <= K <= 8 goes through the small-k kernel."""
     if p1.shape[0] != p2.shape[0]:
         raise ValueError("pts1 and pts2 must have the same batch dimension.")
     if p1.shape[2] != p2.shape[2]:
         raise ValueError("pts1 and pts2 must have the same point dimension.")
-    if K != 1:
-        raise NotImplementedError("reart_b200.knn_points implements K == 1 (what the reference's Chamfer path uses)")
+    if not 1 <= K <= 8:
+        raise NotImplementedError("reart_b200.knn_points implements 1 <= K <= 8 (the reference's Chamfer path uses K == 1)")
     if p1.shape[2] != 3:
         raise ValueError("reart_b200 kernels are specialised for 3-D points (D == 3).")
     _check_full_lengths(lengths1, p1.shape[1], "lengths1")
     _check_full_lengths(lengths2, p2.shape[1], "lengths2")
-    p1_dists, p1_idx = _Knn1.apply(p1, p2)
+    if K == 1:
+        p1_dists, p1_idx = _Knn1.apply(p1, p2)
+    else:
+        # K > 1 is never used by the reference: indices from the small-k kernel (ascending, lowest index on ties);
+        # the squared distances are re-formed in torch from the gathered neighbours, which also gives autograd
+        from . import ops
+        if p2.shape[1] < K:
+            raise ValueError("knn_points: fewer than K points in p2")
+        _, p1_idx = ops.knn(p2, p1, K)
+        nbrs = knn_gather(p2, p1_idx)
+        p1_dists = ((p1[:, :, None, :] - nbrs) ** 2).sum(-1)
     p2_nn = None
     if return_nn:
         p2_nn = knn_gather(p2, p1_idx, lengths2)

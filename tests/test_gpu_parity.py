@@ -776,3 +776,21 @@ def test_register_blocked_topk_and_blend_path_vs_oracle():
         b_o, m_o = oracle.blend_anchor_motion(queries[t].cpu().numpy(), refs[t].cpu().numpy(), flows[t].cpu().numpy())
         np.testing.assert_allclose(B[t].cpu().numpy(), b_o, rtol=1e-4, atol=1e-7)
         assert (M[t].cpu().numpy() == m_o).mean() > 0.999
+
+
+def test_knn_points_k_greater_than_one_with_autograd():
+    from reart_b200.chamfer import knn_points
+    rng = np.random.default_rng(40)
+    a = rng.standard_normal((2, 300, 3)).astype(np.float32); b = rng.standard_normal((2, 500, 3)).astype(np.float32)
+    A = cu(a).requires_grad_(True); Bt = cu(b).requires_grad_(True)
+    nn = knn_points(A, Bt, K=4, return_nn=True)
+    assert nn.dists.shape == (2, 300, 4) and nn.idx.shape == (2, 300, 4) and nn.knn.shape == (2, 300, 4, 3)
+    for bb in range(2):
+        d_o, i_o = oracle.knn(b[bb], a[bb], 4)
+        assert np.array_equal(nn.idx[bb].cpu().numpy(), i_o)
+        np.testing.assert_allclose(nn.dists[bb].detach().cpu().numpy(), d_o ** 2, rtol=1e-5, atol=1e-7)
+    nn.dists.sum().backward()
+    dense = ((A.detach()[:, :, None, :] - Bt.detach()[:, None, :, :]) ** 2).sum(-1)
+    idx = dense.topk(4, dim=2, largest=False).indices
+    gA = (2 * (A.detach()[:, :, None, :] - torch.gather(Bt.detach()[:, None].expand(-1, 300, -1, -1), 2, idx[..., None].expand(-1, -1, -1, 3)))).sum(2)
+    np.testing.assert_allclose(A.grad.cpu().numpy(), gA.cpu().numpy(), rtol=1e-4, atol=1e-5)
