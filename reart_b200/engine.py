@@ -226,3 +226,50 @@ class KinematicEngine(_EngineBase):
 def tau_schedule(i: int, n_iter: int, start_tau: float, end_tau: float) -> float:
     """utils/model_utils.py:33-37 as run_robot.py:86,157 uses it (cur_iter = i + 1)."""
     return end_tau + (start_tau - end_tau) * (math.cos(math.pi * (i + 1) / n_iter) + 1.0) * 0.5
+
+
+def fit_relaxation(cano: torch.Tensor, frames: torch.Tensor, num_parts: int, n_iter: int, ctx: Optional[DistContext] = None,
+                   start_tau: float = 5.0, end_tau: float = 1.0, log_every: int = 0, **engine_kwargs):
+    """The relaxation optimisation of run_robot.py:153-221 (recon loss, cosine tau schedule :86,157) on the engine.
+    Returns (engine, losses) where ``losses`` holds the all-rank loss every ``log_every`` iterations (0: only the
+    last) -- reading it is the only host sync."""
+    eng = RelaxationEngine(cano, frames, num_parts, ctx=ctx, **engine_kwargs)
+    losses = []
+    loss = None
+    for i in range(n_iter):
+        loss = eng.step(tau_schedule(i, n_iter, start_tau, end_tau))
+        if log_every and (i % log_every == 0):
+            losses.append(float(loss))
+    if loss is not None:
+        losses.append(float(loss))
+    return eng, losses
+
+
+def fit_candidates(sequence: torch.Tensor, candidates, num_parts: int, n_iter: int, ctx: Optional[DistContext] = None,
+                   **kwargs):
+    """``cano_idx`` model selection (README.md:60 of the reference: fit every candidate canonical frame, keep the
+    lowest energy).  The fits are independent runs: with G ranks, rank r fits candidates r, r+G, ... on its own GPU
+    with NO communication; one gather of the final energies picks the winner.  ``sequence`` [T+1,N,3] is the
+    complete sequence; candidate c uses frame c as the canonical cloud and the others as observations.
+    Returns (best_cano_idx, {cano_idx: energy}) on every rank."""
+    ctx = ctx or DistContext()
+    mine = {}
+    for k, c in enumerate(candidates):
+        if k % ctx.world_size != ctx.rank:
+            continue
+        cano = sequence[c]
+        frames = torch.cat((sequence[:c], sequence[c + 1:]), dim=0)
+        _, losses = fit_relaxation(cano, frames, num_parts, n_iter, ctx=DistContext(), **kwargs)   # local, unsharded
+        mine[int(c)] = losses[-1]
+    # one exchange of len(candidates) scalars: every rank fills in the energies it computed (+inf elsewhere), MIN-reduce
+    dev = sequence.device if (sequence.is_cuda and ctx.backend != "gloo") else torch.device("cpu")
+    vec = torch.full((len(candidates),), float("inf"), dtype=torch.float64, device=dev)
+    for k, c in enumerate(candidates):
+        if int(c) in mine:
+            vec[k] = mine[int(c)]
+    if ctx.world_size > 1:
+        import torch.distributed as dist
+        dist.all_reduce(vec, op=dist.ReduceOp.MIN)
+    table = {int(c): float(vec[k]) for k, c in enumerate(candidates)}
+    best = min(table.items(), key=lambda kv: (kv[1], kv[0]))[0]
+    return best, table

@@ -794,3 +794,13 @@ def test_knn_points_k_greater_than_one_with_autograd():
     idx = dense.topk(4, dim=2, largest=False).indices
     gA = (2 * (A.detach()[:, :, None, :] - torch.gather(Bt.detach()[:, None].expand(-1, 300, -1, -1), 2, idx[..., None].expand(-1, -1, -1, 3)))).sum(2)
     np.testing.assert_allclose(A.grad.cpu().numpy(), gA.cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_candidate_fits_pick_the_lowest_energy_canonical_frame():
+    """cfg5 logic on one GPU: every candidate cano_idx is an independent fit; the selected one has the lowest energy."""
+    from reart_b200.engine import fit_candidates
+    seq = synthetic_sequence(5, 1024, 3, seed=8)
+    full = np.concatenate([seq["cano"][None], seq["frames"]], axis=0)
+    best, table = fit_candidates(cu(full), [0, 2, 4], num_parts=3, n_iter=30, use_graph=False)
+    assert set(table) == {0, 2, 4} and all(np.isfinite(v) for v in table.values())
+    assert table[best] == min(table.values())
