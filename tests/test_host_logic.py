@@ -228,3 +228,22 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
     assert L.reart_skin_fwd(null, null, null, null, 0, 0, 3, null, null) == 0
     for code in (0, -1, -2, -3, -4, -99):
         assert len(L.reart_error_string(code)) > 0
+
+
+def test_bench_reference_arm_contract_on_cpu():
+    """`bench.py --impl reference` is the CPU arm (oracle port on the host cores): it must run without a GPU and
+    print one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "skinned_chamfer_fwd_bwd_directed_point_pairs_per_s"
+    assert d["unit"] == "pairs/s" and d["higher_is_better"] is True and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and d["dtype"] == "f32" and d["data"] == "synthetic"
