@@ -263,6 +263,169 @@ def gen_flow(ref):
     print("flow.npz", mask.float().mean().item())
 
 
+def _fps_from_zero(xyz, npoint):
+    """CUDA semantics of furthest point sampling (sampling_gpu.cu:113-115 starts at index 0; the reference's CPU
+    fallback starts at a random index).  Used as the FPS stand-in for the structure goldens."""
+    B, N, _ = xyz.shape
+    out = torch.zeros(B, npoint, dtype=torch.long)
+    for b in range(B):
+        dist = torch.full((N,), 1e10)
+        far = 0
+        for i in range(npoint):
+            out[b, i] = far
+            d = ((xyz[b] - xyz[b, far]) ** 2).sum(-1)
+            dist = torch.minimum(dist, d)
+            far = int(torch.argmax(dist))
+    return out
+
+
+def _random_screw_sequence(T, P, gen, prismatic=(), static=()):
+    """[T,P,4,4] rigid transforms: part p moves about its own fixed screw axis (revolute unless listed)."""
+    import importlib
+    se3 = importlib.import_module("screw_se3")
+    out = torch.eye(4).repeat(T, P, 1, 1)
+    for p in range(P):
+        if p in static:
+            continue
+        l = torch.nn.functional.normalize(torch.randn(1, 3, generator=gen), dim=-1)
+        pt = 0.3 * torch.randn(1, 3, generator=gen)
+        m = torch.cross(pt, l, dim=-1)
+        for t in range(T):
+            if p in prismatic:
+                th, d = torch.tensor([1e-6]), 0.05 + 0.3 * torch.rand(1, generator=gen)
+            else:
+                th, d = 0.2 + 1.2 * torch.rand(1, generator=gen), torch.tensor([1e-6])
+            out[t, p] = se3.transform_from_exponential_coordinates(
+                se3.screw_param_to_exponential_coordinates(l, m, th, d))[0]
+    return out
+
+
+def gen_structure(ref):
+    """Structure-extraction stage: utils/graph_utils.py:62-421, utils/kinematic_utils.py:20-148,
+    screw_se3/dq_utils.py:134-182, utils/model_utils.py:92-118 run on (1) the shipped nao relaxation result and
+    (2) a synthetic mixed revolute / prismatic / static sequence."""
+    import importlib
+    import warnings
+    import networkx as nx
+    g = importlib.import_module("utils.graph_utils")
+    k = importlib.import_module("utils.kinematic_utils")
+    mu = ref.model_utils
+    se3 = ref.screw_se3
+    g.farthest_point_sample = _fps_from_zero
+    cd = ref.chamfer.ChamferDistance()
+    warnings.simplefilter("ignore")
+    out = {}
+
+    # ---- (1) nao base-2 result
+    res = pickle.load(open(f"{REF}/demo_data/pretrained/nao/base-2/result_14999.pkl", "rb"))
+    cano = torch.from_numpy(res["cano_pc"]).float()
+    pc_list = torch.from_numpy(res["pc_list"]).float()
+    pose = torch.from_numpy(res["pred_pose_list"]).float()
+    part = torch.from_numpy(res["pred_cano_part"]).long()
+    out["nao_pose"], out["nao_part"], out["nao_cano"] = pose.numpy(), part.numpy().astype(np.int16), cano.numpy()
+    uni = torch.unique(part, sorted=True)
+    out["nao_uni"] = uni.numpy()
+
+    dq = se3.transform_to_dq(pose.reshape(-1, 4, 4))
+    l, m, th, d = se3.dq_to_screw(dq)
+    out["nao_dq"], out["nao_l"], out["nao_m"], out["nao_th"], out["nao_d"] = (x.numpy() for x in (dq, l, m, th, d))
+
+    ax, mo, th, di, rel = g.compute_relative_trans(pose, return_trans=True)
+    sel = lambda x: x[:, uni, :][:, :, uni]
+    geo = g.compute_geo_cost(sel(rel), sel(ax), sel(mo), sel(th), sel(di))
+    out["nao_rel_theta"], out["nao_rel_dist"] = sel(th).numpy(), sel(di).numpy()
+    out["nao_rel_axis"], out["nao_rel_moment"] = sel(ax).numpy(), sel(mo).numpy()
+    out["nao_geo_cost"] = geo.numpy()
+    out["nao_root_cost"] = g.compute_root_cost(pose).numpy()
+
+    pred = mu.compute_pc_transform(cano, pose, part)
+    fps_pts, fps_idx = g.fps_sample_cano(cano, part, uni, num_fps=20)
+    part_fps = g.fps_index_list(pred, fps_idx)
+    cano_dist, pair = g.compute_spatial_cost(fps_pts, cd, return_index=True)
+    P = len(uni)
+    px, py = torch.meshgrid(torch.arange(P), torch.arange(P), indexing="ij")
+    conn_all = torch.stack([px, py], dim=2).reshape(-1, 2)
+    joint = g.compute_joint_cost(part_fps, conn_all, pair.reshape(-1, 2)).reshape(-1, P, P).sum(dim=0)
+    out["nao_fps_idx"], out["nao_cano_dist"], out["nao_pair"], out["nao_joint_cost"] = \
+        fps_idx.numpy(), cano_dist.numpy(), pair.numpy(), joint.numpy()
+
+    merged = g.merging_wrapper(part.clone(), pose, cano, cd, 3e-2, n_it=2)
+    out["nao_merged_part"] = merged.numpy().astype(np.int16)
+    conn = g.mst_wrapper(merged, pose, cano, cd, verbose=False, num_fps=20, cano_dist_thr=1e-2, joint_cost_weight=100)
+    out["nao_connection"] = conn.numpy()
+    new_seg, new_trans, new_conn = k.extract_kinematic(merged, pose, conn.clone())
+    out["nao_new_seg"], out["nao_new_conn"] = new_seg.numpy().astype(np.int16), new_conn.numpy()
+    G, root, axis_list, moment_list, theta_list, edge_index = k.build_graph(new_conn, new_trans, verbose=False)
+    names = list(edge_index.keys())
+    out["nao_root"] = np.int64(root)
+    out["nao_edges"] = np.array([[int(a) for a in n.split("_")] for n in names], np.int64)
+    out["nao_edge_ids"] = np.array([edge_index[n] for n in names], np.int64)
+    out["nao_axis_list"], out["nao_moment_list"], out["nao_theta_list"] = \
+        axis_list.numpy(), moment_list.numpy(), theta_list.numpy()
+    out["nao_reverse_topo"] = np.array(list(reversed(list(nx.topological_sort(G)))), np.int64)
+    out["nao_screw_cost"] = np.float64(g.compute_screw_cost(new_trans, new_conn).item())
+    pred2 = mu.compute_pc_transform(cano, new_trans, new_seg)
+    cidx = int(res["cano_idx"])
+    complete = torch.cat((pred2[:cidx], cano[None], pred2[cidx:]), dim=0)
+    out["nao_group_err"] = np.float64(float(mu.compute_group_temporal_err(complete, new_seg)))
+    sub = torch.arange(0, cano.shape[0], 8)                      # 512-point subsample keeps the Hungarian solves short
+    out["nao_ass_sub"] = sub.numpy()
+    out["nao_ass_err"] = np.float64(mu.compute_ass_err(pred2[:, sub], pc_list[:, sub], use_nproc=False).item())
+
+    # ---- (2) synthetic mixed joints: part 0 static, 2 and 4 prismatic, others revolute; chain 0-1-2, 1-3, 0-4
+    gen = torch.Generator().manual_seed(7)
+    T, P = 6, 5
+    local = _random_screw_sequence(T, P, gen, prismatic=(2, 4), static=(0,))
+    parent = [-1, 0, 1, 1, 0]
+    world = torch.eye(4).repeat(T, P, 1, 1)
+    for p in range(1, P):
+        world[:, p] = torch.bmm(world[:, parent[p]], local[:, p])
+    out["syn_trans"] = world.numpy()
+    T_recon, cost = g.compute_screw_trans(local.clone(), return_cost=True)
+    out["syn_local"], out["syn_recon"], out["syn_recon_cost"] = local.numpy(), T_recon.numpy(), np.float64(cost.item())
+    conn = torch.tensor([[1, 0], [2, 1], [3, 1], [4, 0]])
+    out["syn_conn"] = conn.numpy()
+    out["syn_screw_cost"] = np.float64(g.compute_screw_cost(world, conn).item())
+    ax, mo, th, di, rel = g.compute_relative_trans(world, return_trans=True)
+    out["syn_geo_cost"] = g.compute_geo_cost(rel, ax, mo, th, di).numpy()
+    out["syn_root_cost"] = g.compute_root_cost(world).numpy()
+    G, root, a_l, m_l, t_l, d_l, e_i, jt = k.build_graph(conn.clone(), world, verbose=False, revolute_only=False,
+                                                         return_joint_type=True)
+    names = list(e_i.keys())
+    out["syn_root"] = np.int64(root)
+    out["syn_edges"] = np.array([[int(a) for a in n.split("_")] for n in names], np.int64)
+    out["syn_axis_list"], out["syn_moment_list"] = a_l.numpy(), m_l.numpy()
+    out["syn_theta_list"], out["syn_distance_list"] = t_l.numpy(), d_l.numpy()
+    out["syn_joint_prismatic"] = np.array([j == "prismatic" for j in jt])
+
+    # ---- (3) greedy spanning tree on seeded cost matrices, with and without relabelling / early stop
+    cost = torch.rand(7, 7, generator=gen)
+    cost = cost + cost.T + 1e4 * torch.eye(7)
+    out["mst_cost"] = cost.numpy()
+    out["mst_plain"] = g.mst(cost).numpy()
+    lab = torch.tensor([2, 3, 5, 8, 11, 12, 19])
+    out["mst_labels"] = lab.numpy()
+    out["mst_relabelled"] = g.mst(cost, uni_label=lab).numpy()
+    out["mst_capped"] = g.mst(cost, uni_label=lab, max_cost=0.55).numpy()
+    out["mst_cap"] = np.float64(0.55)
+
+    # ---- (4) merge pass with real contractions: parts {1,2,5} move together, {3,6} move together, 0 and 4 alone
+    T, P = 5, 7
+    motion = _random_screw_sequence(T, 3, gen)
+    trans = torch.eye(4).repeat(T, P, 1, 1)
+    for p, grp in {1: 0, 2: 0, 5: 0, 3: 1, 6: 1, 4: 2}.items():
+        trans[:, p] = motion[:, grp]
+    seg = torch.randint(0, P, (300,), generator=gen)
+    conn = torch.tensor([[0, 1], [2, 1], [2, 5], [5, 3], [3, 6], [4, 0]])
+    m_seg, m_conn = g.merge_graph(seg.clone(), conn, trans, 3e-2, verbose=False)
+    out["mrg_trans"], out["mrg_seg"], out["mrg_conn"] = trans.numpy(), seg.numpy(), conn.numpy()
+    out["mrg_new_seg"], out["mrg_new_conn"] = m_seg.numpy(), m_conn.numpy()
+
+    np.savez_compressed(os.path.join(OUT, "structure.npz"), **out)
+    print("structure.npz", out["nao_connection"].tolist(), out["nao_root"], out["nao_screw_cost"],
+          out["syn_joint_prismatic"], out["mst_capped"].shape)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -272,6 +435,7 @@ def main():
     gen_fk(ref)
     gen_flow(ref)
     gen_nao(ref)
+    gen_structure(ref)
 
 
 if __name__ == "__main__":

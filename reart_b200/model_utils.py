@@ -48,3 +48,46 @@ def compute_pc_transform(cano_pc, pose_list, cano_part):
     tr = pose_list[:, :, :3, 3]
     W = F.one_hot(cano_part, num_classes=num_parts)
     return ops.skin(cano_pc, W, R, tr)
+
+
+def compute_align_trans(trans_list: torch.Tensor, root_trans: torch.Tensor) -> torch.Tensor:
+    """utils/model_utils.py:121-126 -- express every part motion in the root's frame: (T,P,4,4), (T,4,4) -> (T,P,4,4)."""
+    from .screw_se3 import inverse_transformation
+    return torch.matmul(inverse_transformation(root_trans)[:, None], trans_list)
+
+
+def compute_ass_err(pc_trans_list: torch.Tensor, pc_list: torch.Tensor, use_nproc: bool = True) -> torch.Tensor:
+    """utils/model_utils.py:92-103 -- model-selection term (run_robot.py:306): mean squared distance of the optimal
+    one-to-one matching between each posed cloud and its observed frame, (T,N,3) x2 -> scalar.
+
+    The Euclidean cost stays a torch op, the T Hungarian solves run on the host (scipy, as in the reference) in a
+    thread pool instead of a process pool spawned per call; the matched pairs are gathered on the device.
+    """
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from scipy.optimize import linear_sum_assignment
+    cost = torch.cdist(pc_trans_list, pc_list).cpu().numpy()
+    if use_nproc and len(cost) > 1:
+        with ThreadPoolExecutor(max_workers=min(len(cost), 16)) as pool:
+            pairs = list(pool.map(linear_sum_assignment, cost))
+    else:
+        pairs = [linear_sum_assignment(c) for c in cost]
+    rows = torch.from_numpy(np.stack([r for r, _ in pairs])).to(pc_list.device)
+    cols = torch.from_numpy(np.stack([c for _, c in pairs])).to(pc_list.device)
+    a = torch.gather(pc_trans_list, 1, rows[:, :, None].expand(-1, -1, 3))
+    b = torch.gather(pc_list, 1, cols[:, :, None].expand(-1, -1, 3))
+    return (a - b).square().sum(dim=-1).mean()
+
+
+def compute_group_temporal_err(pc_list: torch.Tensor, seg_part: torch.Tensor) -> torch.Tensor:
+    """utils/model_utils.py:106-118 -- model-selection term (run_robot.py:311): the largest, over parts, mean squared
+    distance of a part's points to the part's per-frame centroid: (T,N,3), (N,) -> scalar.  One segmented reduction
+    over all parts (the reference loops over parts with an ``.item()`` each)."""
+    labels, inverse = torch.unique(seg_part, sorted=True, return_inverse=True)
+    P, T = labels.numel(), pc_list.shape[0]
+    counts = torch.bincount(inverse, minlength=P).to(pc_list.dtype)
+    sums = torch.zeros(T, P, 3, dtype=pc_list.dtype, device=pc_list.device).index_add_(1, inverse, pc_list)
+    centroid = sums / counts[None, :, None]
+    sq = (pc_list - centroid[:, inverse]).square().sum(dim=2)                                  # (T,N)
+    per_part = torch.zeros(T, P, dtype=pc_list.dtype, device=pc_list.device).index_add_(1, inverse, sq).sum(dim=0)
+    return (per_part / (counts * T)).max()
