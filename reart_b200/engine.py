@@ -116,7 +116,8 @@ class RelaxationEngine(_EngineBase):
                  trans_lr: float = 1e-2, seg_lr: float = 1e-3, weight_decay: float = 0.0, use_graph: bool = True,
                  seed: int = 2, flow_ref=None, cano_idx: int = 0, lambda_flow: float = 1.0, robust_flow: bool = False):
         """flow_ref: optional ``flow_utils.FlowReference`` (run_robot.py:78-84) enabling the flow loss of
-        run_robot.py:194-213 (single rank only: consecutive frames couple across shard boundaries)."""
+        run_robot.py:194-213.  Consecutive frames couple across shard boundaries: under frame sharding each rank
+        receives one skinned frame per iteration from the previous rank (``dist.halo_from_previous_rank``)."""
         super().__init__(ctx, use_graph)
         self.flow_ref, self.cano_idx, self.lambda_flow, self.robust_flow = flow_ref, cano_idx, lambda_flow, robust_flow
         # the flow loss couples consecutive frames: under frame sharding each rank evaluates the pairs whose second

@@ -392,10 +392,10 @@ class _SkinnedChamfer(Function):
         gW, gR, gtr = ctx.grads
         if gW is None:
             return None, None, None, None, None, None, None
-        if ctx.unit_grad:
-            pass                                               # caller promised d(objective)/d(loss) == 1: no scaling launch
-        elif g_loss is None:
+        if g_loss is None:                                     # the loss itself is not part of the objective
             gW, gR, gtr = torch.zeros_like(gW), torch.zeros_like(gR), torch.zeros_like(gtr)
+        elif ctx.unit_grad:
+            pass                                               # caller promised d(objective)/d(loss) == 1: no scaling launch
         else:
             gW, gR, gtr = torch._foreach_mul([gW, gR, gtr], g_loss)          # one launch for the three
         if g_skinned is not None:
