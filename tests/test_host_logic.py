@@ -32,6 +32,36 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert L.reart_packed_bytes(1, 33) >= 64 * 12
 
 
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Argument count and the int64 / int / float / pointer class of every parameter, parsed from the header."""
+    import ctypes
+    from reart_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "reart_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    protos = re.findall(r"REART_API\s+([\w\s\*]+?)\b(reart_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S)
+    assert len(protos) == len(_lib.SIGNATURES)
+
+    def kind(decl):
+        decl = decl.strip()
+        if "*" in decl:
+            return "ptr"
+        for key in ("int64_t", "float", "double", "int"):
+            if re.search(rf"\b{key}\b", decl):
+                return key
+        raise AssertionError(decl)
+
+    ctype_kind = {ctypes.c_int64: "int64_t", ctypes.c_int: "int", ctypes.c_float: "float", ctypes.c_void_p: "ptr",
+                  ctypes.c_char_p: "ptr"}
+    for ret, name, params in protos:
+        restype, argtypes = _lib.SIGNATURES[name]
+        decls = [] if params.strip() in ("", "void") else [p for p in params.split(",")]
+        assert len(decls) == len(argtypes), name
+        for d, a in zip(decls, argtypes):
+            assert kind(d) == ctype_kind.get(a, "ptr"), (name, d.strip(), a)
+        assert kind(ret + " ") == ctype_kind.get(restype, "ptr"), (name, ret)
+
+
 def test_header_cites_reference_for_every_entry_point():
     src = open(os.path.join(ROOT, "include", "reart_b200.h")).read()
     for name in ("utils/chamfer.py:174", "utils/chamfer.py:206", "networks/model.py:63-69", "networks/loss.py:24-29",
