@@ -426,6 +426,58 @@ def gen_structure(ref):
           out["syn_joint_prismatic"], out["mst_capped"].shape)
 
 
+def gen_nao_eval(ref):
+    """KAT-E: the rows of result.txt that the UNMODIFIED run_robot.py --evaluate writes for the
+    shipped nao checkpoints (run_robot.py:224-338), produced by scripts/run_reference_dropin.py --backend stubs in this
+    container, together with the dataset-side inputs of that evaluation (ground-truth flow / clouds / parts, the three
+    sparse novel states of ik(), the kinematic-2 tree), so that a GPU test can reproduce the rows without the reference
+    tree."""
+    import importlib
+    import json
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rows = {}
+    # base_fps0: the reference's CUDA FPS kernel starts at index 0, its CPU fallback at torch.randint (SURVEY Q13), and the
+    # structure stage of the relaxation evaluation depends on the samples -- "base" is the CPU row of BASELINE.md, "base_fps0"
+    # what the same reference code gives with the CUDA start index (= what it prints on a GPU box over the drop-in)
+    for tag, model, ck, extra in (("kin", "kinematic", "kinematic-2", []), ("base", "base", "base-2", []),
+                                  ("base_fps0", "base", "base-2", ["--fps-from-zero"])):
+        tmp = tempfile.mkdtemp()
+        summ = os.path.join(tmp, "s.json")
+        subprocess.check_call([sys.executable, os.path.join(root, "scripts", "run_reference_dropin.py"), "--backend", "stubs",
+                               *extra, "--ref-root", REF, "--summary", summ, "--", f"--seq_path={REF}/demo_data/data/nao",
+                               f"--save_root={tmp}", "--cano_idx=2", "--evaluate", f"--model={model}",
+                               f"--resume={REF}/demo_data/pretrained/nao/{ck}/model.pth.tar"],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        rows[tag] = json.load(open(summ))["result_txt"]
+    ds = importlib.import_module("dataset.dataset_robot")
+    du = importlib.import_module("utils.dataset_utils")
+    dataset = ds.Sequence(f"{REF}/demo_data/data/nao", num_points=4096, cano_idx=2)
+    sample = dataset[0]
+    cano_pose = dataset.pose_list[dataset.cano_idx]
+    states = [du.sparse_sample_novel_state(sample["cano_pc"], sample["gt_cano_part"], cano_pose, nov, sparse_sample_per_part=1)
+              for nov in dataset.novel_pose_list]
+    ck = torch.load(f"{REF}/demo_data/pretrained/nao/kinematic-2/model.pth.tar", map_location="cpu", weights_only=False)
+    tree = {"edge_index": {k: int(v) for k, v in ck["edge_index"].items()},
+            "paths_to_base": {str(int(k)): [int(x) for x in v] for k, v in ck["paths_to_base"].items()},
+            "reverse_topo": [int(x) for x in ck["reverse_topo"]]}
+    out = dict(gt_flow_list=sample["gt_flow_list"].astype(np.float32),
+               complete_gt_pc_list=sample["complete_gt_pc_list"].astype(np.float32),
+               gt_cano_part=np.asarray(sample["gt_cano_part"]).astype(np.int16),
+               sparse_cano_pc=np.asarray(states[0]["sparse_cano_pc"], np.float32),
+               sparse_novel_pc=np.stack([np.asarray(s["sparse_novel_pc"], np.float32) for s in states]),
+               novel_pc=np.stack([np.asarray(s["novel_pc"], np.float32) for s in states]),
+               kin_tree_json=np.array(json.dumps(tree)),
+               kin_rows_json=np.array(json.dumps(rows["kin"])), base_rows_json=np.array(json.dumps(rows["base"])),
+               base_rows_fps0_json=np.array(json.dumps(rows["base_fps0"])))
+    for s in states[1:]:
+        assert np.array_equal(s["sparse_cano_pc"], states[0]["sparse_cano_pc"])
+    np.savez_compressed(os.path.join(OUT, "nao_eval.npz"), **out)
+    print("nao_eval.npz", rows)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -436,6 +488,7 @@ def main():
     gen_flow(ref)
     gen_nao(ref)
     gen_structure(ref)
+    gen_nao_eval(ref)
 
 
 if __name__ == "__main__":

@@ -358,15 +358,19 @@ def merge_graph(seg_part, joint_connection, trans_list, merge_thr, verbose: bool
     return new_part, new_connection
 
 
-def _pair_costs(seg_part, trans_list, cano_pc, chamfer_dist, num_fps, fps):
+def _pair_costs(seg_part, trans_list, cano_pc, chamfer_dist, num_fps, fps, pose_labels=None):
     """Shared front half of merging_wrapper / mst_wrapper: canonical closest approach of every part pair and the
-    drift of that joint-anchor pair over time.  Labels are hard, so a sample of part p moves with T[:, p] alone:
-    only the P x num_fps samples are posed (the reference skins the whole cloud first, graph_utils.py:370,399)."""
+    drift of that joint-anchor pair over time.  Labels are hard, so a sample moves with ONE transform: only the
+    P x num_fps samples are posed (the reference skins the whole cloud first, graph_utils.py:370,399).
+    ``pose_labels`` are the per-point labels the reference skinned the cloud with: in merging_wrapper that happens
+    ONCE before the merge rounds (graph_utils.py:370), so from round 2 on a point absorbed from part b still moves
+    with T_b, not with the transform of the part that swallowed it."""
     uni_label = torch.unique(seg_part, sorted=True)
     P = uni_label.numel()
-    fps_pts, _ = fps_sample_cano(cano_pc, seg_part, uni_label, num_fps=num_fps, fps=fps)
-    R, t = trans_list[:, uni_label, :3, :3], trans_list[:, uni_label, :3, 3]
-    part_fps = torch.einsum("tpij,psj->tpsi", R, fps_pts) + t[:, :, None, :]
+    fps_pts, fps_idx = fps_sample_cano(cano_pc, seg_part, uni_label, num_fps=num_fps, fps=fps)
+    mover = (seg_part if pose_labels is None else pose_labels)[fps_idx]                 # (P, S) transform id per sample
+    R, t = trans_list[:, mover, :3, :3], trans_list[:, mover, :3, 3]                   # (T,P,S,3,3), (T,P,S,3)
+    part_fps = torch.einsum("tpsij,psj->tpsi", R, fps_pts) + t
     cano_dist, pair = compute_spatial_cost(fps_pts, chamfer_dist, return_index=True)
     ids = torch.arange(P, device=pair.device)
     all_pairs = torch.stack(torch.meshgrid(ids, ids, indexing="ij"), dim=2).reshape(-1, 2)
@@ -376,9 +380,11 @@ def _pair_costs(seg_part, trans_list, cano_pc, chamfer_dist, num_fps, fps):
 
 def merging_wrapper(seg_part, trans_list, cano_pc, chamfer_dist, merge_thr, n_it: int = 2, fps=None):
     """graph_utils.py:369-394 -- ``n_it`` rounds of: spanning tree on (closest approach + joint drift), then
-    ``merge_graph``."""
+    ``merge_graph``.  The cloud is posed with the labels at entry in every round (graph_utils.py:370)."""
+    entry_labels = seg_part
     for _ in range(n_it):
-        uni_label, cano_dist, joint_cost = _pair_costs(seg_part, trans_list, cano_pc, chamfer_dist, 20, fps)
+        uni_label, cano_dist, joint_cost = _pair_costs(seg_part, trans_list, cano_pc, chamfer_dist, 20, fps,
+                                                       pose_labels=entry_labels)
         cost = cano_dist + joint_cost
         cost = cost + 1e4 * torch.eye(cost.shape[0], device=cost.device, dtype=cost.dtype)
         candidates = mst(cost, uni_label=uni_label)
