@@ -96,12 +96,16 @@ REART_API int reart_pack_cloud(const float* pts, int64_t B, int64_t P, float* pa
  * networks/model.py:161-165 (KinematicModel.forward) and utils/model_utils.py:54-67 (compute_pc_transform):
  *   out[t,n,:] = sum_p W[n,p] * (R[t,p] @ cano[n] + tr[t,p])
  * cano [N,3], W [N,P] float32, R [T,P,3,3], tr [T,P,3] -> out [T,N,3].
- * Backward: g [T,N,3] -> gW [N,P], gR [T,P,3,3], gtr [T,P,3] (all overwritten).
+ * Backward: g [T,N,3] -> gW [N,P], gR [T,P,3,3], gtr [T,P,3] (all overwritten).  One pass over g, no atomics:
+ * per-chunk pose partials go through the caller's workspace (reart_skin_bwd_workspace_bytes) and are reduced in a
+ * fixed order, so the result is bit-identical from run to run.
  * ------------------------------------------------------------------------------------------- */
 REART_API int reart_skin_fwd(const float* cano, const float* W, const float* R, const float* tr, int64_t T, int64_t N,
                              int64_t P, float* out, void* stream);
+REART_API int64_t reart_skin_bwd_workspace_bytes(int64_t T, int64_t N, int64_t P);
 REART_API int reart_skin_bwd(const float* cano, const float* W, const float* R, const float* tr, const float* g,
-                             int64_t T, int64_t N, int64_t P, float* gW, float* gR, float* gtr, void* stream);
+                             int64_t T, int64_t N, int64_t P, float* gW, float* gR, float* gtr, void* workspace,
+                             int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * The whole per-iteration energy, fused: skin -> bidirectional Chamfer -> sum -> backward to the
@@ -117,6 +121,15 @@ REART_API int reart_skinned_chamfer_fwd_bwd(const float* cano, const float* W, c
                                             const float* tgt, const float* tgt_packed, int64_t T, int64_t N, int64_t M,
                                             int64_t P, float* skinned, double* loss, float* gW, float* gR, float* gtr,
                                             float* g_skinned, int compute_grad, void* workspace,
+                                            int64_t workspace_bytes, void* stream);
+/* Same call with the per-point squared distances and arg-min indices of both directions as optional outputs
+ * (d_fwd/i_fwd [T,N], d_bwd/i_bwd [T,M]; any may be null): what ChamferDistance(..., return_index=True) of
+ * utils/chamfer.py:97-103,119-123 returns, from inside the fused evaluation. */
+REART_API int reart_skinned_chamfer_fwd_bwd_ex(const float* cano, const float* W, const float* R, const float* tr,
+                                            const float* tgt, const float* tgt_packed, int64_t T, int64_t N, int64_t M,
+                                            int64_t P, float* skinned, double* loss, float* gW, float* gR, float* gtr,
+                                            float* g_skinned, int compute_grad, float* d_fwd,
+                                               int64_t* i_fwd, float* d_bwd, int64_t* i_bwd, void* workspace,
                                             int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -136,6 +149,43 @@ REART_API int reart_gumbel_st_fwd(const float* logits, const float* expo, const 
                                   float* W, float* ysoft, void* stream);
 REART_API int reart_gumbel_st_bwd(const float* ysoft, const float* tau, const float* gW, int64_t N, int64_t P,
                                   float* glogits, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The frame-independent part of one relaxation iteration (run_robot.py:154-221, --model=base), fused.
+ * head: seg MLP forward (networks/blocks.py:99-118 via networks/model.py:42-43) + straight-through gumbel-softmax
+ *       weights from caller-drawn Exponential(1) noise `expo` (F.gumbel_softmax(hard=True), networks/model.py:44)
+ *       + 6D -> R (networks/model.py:60).  cano [N,3]; w0 [H,3], b0 [H], w2 [P,H]; expo [N,P]; tau [1]; d6 [T,P,6]
+ *       -> logits [N,P] (optional), W [N,P], ysoft [N,P], R [T,P,3,3].
+ * tail: gumbel backward + seg MLP backward + 6D backward + (frames sharded over `world` ranks: the one-shot
+ *       peer-memory all-reduce of reart_allreduce_oneshot, inline) + Adam with torch.optim.Adam semantics
+ *       (run_robot.py:146-150, 219-221) on w0/b0/w2 (lr_seg) and d6/tr (lr_pose), all in ONE launch with a fixed
+ *       summation order (bit-reproducible).  `tickets` [2] must be zero before the first call only.
+ *       phase 0: everything; phase 1: gradients -> bucket only (caller reduces the bucket, e.g. with NCCL);
+ *       phase 2: Adam from the reduced bucket.
+ * ------------------------------------------------------------------------------------------- */
+REART_API int reart_relax_head(const float* cano, const float* w0, const float* b0, const float* w2, const float* expo,
+                               const float* tau, const float* d6, int64_t N, int64_t H, int64_t P, int64_t T,
+                               float* logits, float* W, float* ysoft, float* R, void* stream);
+typedef struct reart_relax_tail_args {
+    const float* cano;
+    float* w0; float* b0; float* w2;
+    const float* ysoft; const float* tau; const float* gW;
+    float* d6; float* tr;
+    const float* gR; const float* gtr;
+    float* m_seg; float* v_seg; float* m_d6; float* v_d6; float* m_tr; float* v_tr;
+    float* step;
+    float lr_pose, lr_seg, beta1, beta2, eps, weight_decay;
+    float* partials;              /* reart_relax_tail_workspace_bytes(N,H,P) */
+    uint32_t* tickets;
+    const double* loss_local;
+    float* bucket;                /* [4H + PH + 1] */
+    float* loss_out;
+    const uint64_t* peer_base; uint32_t* epoch; int32_t rank, world, n_pad;
+    int32_t phase;
+    int64_t N, H, P, T;
+} reart_relax_tail_args;
+REART_API int64_t reart_relax_tail_workspace_bytes(int64_t N, int64_t H, int64_t P);
+REART_API int reart_relax_tail(const reart_relax_tail_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * 6D rotation representation -> matrix (Gram-Schmidt).

@@ -32,10 +32,13 @@ SIGNATURES = {
     "reart_packed_bytes": (_c_i64, [_c_i64, _c_i64]),
     "reart_pack_cloud": (_c_int, [_vp, _c_i64, _c_i64, _vp, _vp]),
     "reart_skin_fwd": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp]),
-    "reart_skin_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp, _vp]),
+    "reart_skin_bwd_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i64]),
+    "reart_skin_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp, _vp, _c_i64, _vp]),
     "reart_energy_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i64]),
     "reart_skinned_chamfer_fwd_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _c_i64, _vp, _vp,
                                                _vp, _vp, _vp, _vp, _c_int, _vp, _c_i64, _vp]),
+    "reart_skinned_chamfer_fwd_bwd_ex": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _c_i64, _vp, _vp,
+                                                  _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _c_i64, _vp]),
     "reart_segmlp_fwd": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp]),
     "reart_segmlp_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp, _vp]),
     "reart_gumbel_st_fwd": (_c_int, [_vp, _vp, _vp, _c_i64, _c_i64, _vp, _vp, _vp]),
@@ -55,6 +58,24 @@ SIGNATURES = {
     "reart_fp32_probe": (_c_int, [_c_int, _c_int, _c_int, _vp, _vp, ctypes.POINTER(ctypes.c_double),
                                   ctypes.POINTER(ctypes.c_double), _vp]),
 }
+
+
+
+class RelaxTailArgs(ctypes.Structure):
+    """reart_relax_tail_args of include/reart_b200.h (field for field)."""
+    _fields_ = [(n, _vp) for n in ("cano", "w0", "b0", "w2", "ysoft", "tau", "gW", "d6", "tr", "gR", "gtr", "m_seg", "v_seg",
+                                   "m_d6", "v_d6", "m_tr", "v_tr", "step")] + \
+               [(n, ctypes.c_float) for n in ("lr_pose", "lr_seg", "beta1", "beta2", "eps", "weight_decay")] + \
+               [(n, _vp) for n in ("partials", "tickets", "loss_local", "bucket", "loss_out", "peer_base", "epoch")] + \
+               [(n, ctypes.c_int32) for n in ("rank", "world", "n_pad", "phase")] + \
+               [(n, _c_i64) for n in ("N", "H", "P", "T")]
+
+
+SIGNATURES.update({
+    "reart_relax_head": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp, _vp, _vp]),
+    "reart_relax_tail_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i64]),
+    "reart_relax_tail": (_c_int, [ctypes.POINTER(RelaxTailArgs), _vp]),
+})
 
 _lib = None
 

@@ -31,6 +31,7 @@ struct Carver {
 
 inline int64_t packed_bytes(int64_t B, int64_t P) { return align_up(B * packed_floats_per_batch(P) * 4); }
 inline int64_t keys_bytes(int64_t B, int64_t P) { return align_up(B * P * 8); }
+inline int64_t xq_floats(int64_t B, int64_t n_pad_sorted) { return B * (n_pad_sorted / kSortedChunk) * kQuantiles; }
 
 }  // namespace
 
@@ -85,7 +86,7 @@ int reart_knn1_fwd(const float* p1, const float* p2, int64_t B, int64_t P1, int6
 int64_t reart_chamfer_workspace_bytes(int64_t B, int64_t N, int64_t M) {
     if (B < 0 || N < 0 || M < 0) return -1;
     return align_up(B * round_up(N, 256) * 12) + packed_bytes(B, M) + keys_bytes(B, N) + keys_bytes(B, M) +
-           align_up(B * round_up(N, 256)) + kAlign;
+           align_up(B * round_up(N, 256)) + align_up(xq_floats(B, round_up(N, 256)) * 4) + kAlign;
 }
 
 int reart_chamfer_bidir_fwd(const float* src, const float* tgt, int64_t B, int64_t N, int64_t M, float* d_fwd,
@@ -110,8 +111,9 @@ int reart_chamfer_bidir_fwd(const float* src, const float* tgt, int64_t B, int64
     u64* kf = ws.take<u64>(B * N);
     u64* kb = ws.take<u64>(B * M);
     unsigned char* perm = ws.take<unsigned char>(B * n_pad_sorted);
+    float* xq = ws.take<float>(xq_floats(B, n_pad_sorted));
     if (!ws.ok) return REART_ERR_WORKSPACE;
-    int rc = launch_pack_cloud_sorted(src, psrc, perm, B, N, n_pad_sorted, stream);
+    int rc = launch_pack_cloud_sorted(src, psrc, perm, xq, B, N, n_pad_sorted, stream);
     if (rc) return rc;
     rc = launch_pack_cloud(tgt, ptgt, B, M, stream);
     if (rc) return rc;
@@ -126,7 +128,7 @@ int reart_chamfer_bidir_fwd(const float* src, const float* tgt, int64_t B, int64
     p.ndir = 2;
     p.B = (int)B;
     p.dir[0] = KnnDir{src, ptgt, kf, d_fwd, i_fwd, (int)N, (int)M, (int)padded_points(M), 0, 0, 0, kChunk, nullptr};
-    p.dir[1] = KnnDir{tgt, psrc, kb, d_bwd, i_bwd, (int)M, (int)N, (int)n_pad_sorted, 0, 0, 0, sp.col_chunk_pts, perm};
+    p.dir[1] = KnnDir{tgt, psrc, kb, d_bwd, i_bwd, (int)M, (int)N, (int)n_pad_sorted, 0, 0, 0, sp.col_chunk_pts, perm, xq};
     return launch_knn1_finalize(p, stream);
 }
 
@@ -184,26 +186,47 @@ int reart_skin_fwd(const float* cano, const float* W, const float* R, const floa
     return launch_skin_fwd(cano, W, R, tr, T, N, P, out, nullptr, static_cast<cudaStream_t>(stream_));
 }
 
+int64_t reart_skin_bwd_workspace_bytes(int64_t T, int64_t N, int64_t P) {
+    if (T < 0 || N < 0 || P < 0) return -1;
+    return align_up(skin_bwd_workspace_floats(T, N, P) * 4) + kAlign;
+}
+
 int reart_skin_bwd(const float* cano, const float* W, const float* R, const float* tr, const float* g, int64_t T,
-                   int64_t N, int64_t P, float* gW, float* gR, float* gtr, void* stream_) {
+                   int64_t N, int64_t P, float* gW, float* gR, float* gtr, void* workspace, int64_t workspace_bytes,
+                   void* stream_) {
     if (T < 0 || N < 0 || P < 0 || !fits_int(T) || !fits_int(N)) return REART_ERR_INVALID_ARG;
     if ((N * P > 0 && !gW) || (T * P > 0 && (!gR || !gtr))) return REART_ERR_INVALID_ARG;
     if (T > 0 && N > 0 && (!cano || !W || !R || !tr || !g)) return REART_ERR_INVALID_ARG;
-    return launch_skin_bwd(cano, W, R, tr, g, T, N, P, gW, gR, gtr, static_cast<cudaStream_t>(stream_));
+    Carver ws(workspace, workspace_bytes);
+    float* partials = ws.take<float>(skin_bwd_workspace_floats(T, N, P));
+    if (!ws.ok) return REART_ERR_WORKSPACE;
+    return launch_skin_bwd(cano, W, R, tr, g, T, N, P, gW, gR, gtr, partials, static_cast<cudaStream_t>(stream_));
 }
 
 int64_t reart_energy_workspace_bytes(int64_t T, int64_t N, int64_t M) {
     if (T < 0 || N < 0 || M < 0) return -1;
     return align_up(T * round_up(N, 256) * 12) + keys_bytes(T, N) + keys_bytes(T, M) + align_up(T * N * 12) +
-           align_up(T * round_up(N, 256)) + kAlign;
+           align_up(T * round_up(N, 256)) + align_up(xq_floats(T, round_up(N, 256)) * 4) +
+           align_up(T * N * 24 + 64) + align_up(2 * (int64_t)energy_max_blocks() * 8) +
+           align_up(skin_bwd_workspace_floats(T, N, 32) * 4) + kAlign;
 }
 
 int reart_skinned_chamfer_fwd_bwd(const float* cano, const float* W, const float* R, const float* tr, const float* tgt,
                                   const float* tgt_packed, int64_t T, int64_t N, int64_t M, int64_t P, float* skinned,
                                   double* loss, float* gW, float* gR, float* gtr, float* g_skinned, int compute_grad,
                                   void* workspace, int64_t workspace_bytes, void* stream_) {
+    return reart_skinned_chamfer_fwd_bwd_ex(cano, W, R, tr, tgt, tgt_packed, T, N, M, P, skinned, loss, gW, gR, gtr, g_skinned,
+                                            compute_grad, nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes, stream_);
+}
+
+int reart_skinned_chamfer_fwd_bwd_ex(const float* cano, const float* W, const float* R, const float* tr, const float* tgt,
+                                     const float* tgt_packed, int64_t T, int64_t N, int64_t M, int64_t P, float* skinned,
+                                     double* loss, float* gW, float* gR, float* gtr, float* g_skinned, int compute_grad,
+                                     float* d_fwd, int64_t* i_fwd, float* d_bwd, int64_t* i_bwd, void* workspace,
+                                     int64_t workspace_bytes, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (T <= 0 || N <= 0 || M <= 0 || P <= 0 || !fits_int(T) || !fits_int(padded_points(N)) || !fits_int(padded_points(M)))
+    if (T <= 0 || N <= 0 || M <= 0 || P <= 0 || P > 32 || !fits_int(T) || !fits_int(padded_points(N)) ||
+        !fits_int(padded_points(M)))
         return REART_ERR_INVALID_ARG;
     if (!cano || !W || !R || !tr || !tgt || !tgt_packed || !skinned || !loss) return REART_ERR_INVALID_ARG;
     if (compute_grad && (!gW || !gR || !gtr)) return REART_ERR_INVALID_ARG;
@@ -215,24 +238,35 @@ int reart_skinned_chamfer_fwd_bwd(const float* cano, const float* W, const float
     u64* kb = ws.take<u64>(T * M);
     float* gs = g_skinned ? g_skinned : ws.take<float>(T * N * 3);
     unsigned char* perm = ws.take<unsigned char>(T * n_pad_sorted);
+    float* xq = ws.take<float>(xq_floats(T, n_pad_sorted));
+    // [acc | ticket | col_bound]: the words that must be zero before the search, cleared by ONE memset
+    const int64_t zero_bytes = T * N * 24 + 64;
+    char* zero = ws.take<char>(zero_bytes);
+    double* partials = ws.take<double>(2 * (int64_t)energy_max_blocks());
+    float* bwd_partials = compute_grad ? ws.take<float>(skin_bwd_workspace_floats(T, N, P)) : nullptr;
     if (!ws.ok) return REART_ERR_WORKSPACE;
-    int rc = launch_skin_fwd_sorted(cano, W, R, tr, T, N, P, skinned, psrc, perm, n_pad_sorted, stream);
+    long long* acc = reinterpret_cast<long long*>(zero);
+    unsigned* ticket = reinterpret_cast<unsigned*>(zero + T * N * 24);
+    unsigned* col_bound = ticket + 1;
+    if (cudaMemsetAsync(zero, 0, (size_t)zero_bytes, stream) != cudaSuccess) return REART_ERR_LAUNCH;
+    int rc = launch_skin_fwd_sorted(cano, W, R, tr, T, N, P, skinned, psrc, perm, xq, n_pad_sorted, stream);
     if (rc) return rc;
     SymParams sp = {};
     sp.a = skinned; sp.b_packed = tgt_packed; sp.keys_a = ka; sp.keys_b = kb;
     sp.B = (int)T; sp.na = (int)N; sp.nb = (int)M; sp.nb_pad = (int)padded_points(M);
+    sp.col_bound = col_bound;
     rc = launch_chamfer_sym(sp, stream);
     if (rc) return rc;
-    if (cudaMemsetAsync(loss, 0, sizeof(double), stream) != cudaSuccess) return REART_ERR_LAUNCH;
     EnergyParams ep = {};
     ep.src = skinned; ep.tgt = tgt; ep.src_packed = psrc; ep.tgt_packed = tgt_packed; ep.keys_a = ka; ep.keys_b = kb;
     ep.B = (int)T; ep.N = (int)N; ep.M = (int)M; ep.n_pad = (int)n_pad_sorted; ep.m_pad = (int)padded_points(M);
     ep.row_chunk_pts = kChunk; ep.col_chunk_pts = sp.col_chunk_pts; ep.gscale = 1.0f; ep.g_src = gs; ep.loss = loss;
     if (sp.col_chunk_pts != 256) return REART_ERR_UNSUPPORTED;       // the sorted copy is built per 256-point chunk
-    ep.src_perm = perm;
+    ep.d_fwd = d_fwd; ep.i_fwd = i_fwd; ep.d_bwd = d_bwd; ep.i_bwd = i_bwd;
+    ep.src_perm = perm; ep.src_xq = xq; ep.acc = acc; ep.col_bound = col_bound; ep.partials = partials; ep.ticket = ticket;
     rc = launch_energy_bwd(ep, stream);
     if (rc || !compute_grad) return rc;
-    return launch_skin_bwd(cano, W, R, tr, gs, T, N, P, gW, gR, gtr, stream);
+    return launch_skin_bwd(cano, W, R, tr, gs, T, N, P, gW, gR, gtr, bwd_partials, stream);
 }
 
 int reart_segmlp_fwd(const float* x, const float* w0, const float* b0, const float* w2, int64_t N, int64_t H, int64_t P,
@@ -273,6 +307,42 @@ int reart_gumbel_st_bwd(const float* ysoft, const float* tau, const float* gW, i
     if (!ysoft || !tau || !gW || !glogits) return REART_ERR_INVALID_ARG;
     return launch_gumbel_st(nullptr, nullptr, tau, gW, N, P, nullptr, const_cast<float*>(ysoft), glogits,
                             static_cast<cudaStream_t>(stream_));
+}
+
+int reart_relax_head(const float* cano, const float* w0, const float* b0, const float* w2, const float* expo,
+                     const float* tau, const float* d6, int64_t N, int64_t H, int64_t P, int64_t T, float* logits,
+                     float* W, float* ysoft, float* R, void* stream_) {
+    if (N < 0 || T < 0 || H <= 0 || P <= 0 || !fits_int(4 * N) || !fits_int(T * P)) return REART_ERR_INVALID_ARG;
+    if (N > 0 && (!cano || !w0 || !b0 || !w2 || !expo || !tau || !W || !ysoft)) return REART_ERR_INVALID_ARG;
+    if (T > 0 && (!d6 || !R)) return REART_ERR_INVALID_ARG;
+    return launch_relax_head(cano, w0, b0, w2, expo, tau, d6, N, H, P, T, logits, W, ysoft, R,
+                             static_cast<cudaStream_t>(stream_));
+}
+
+int64_t reart_relax_tail_workspace_bytes(int64_t N, int64_t H, int64_t P) {
+    if (N < 0 || H <= 0 || P <= 0) return -1;
+    return align_up(relax_tail_workspace_floats(N, H, P) * 4) + kAlign;
+}
+
+int reart_relax_tail(const reart_relax_tail_args* x, void* stream_) {
+    if (!x || x->N <= 0 || x->T <= 0 || x->H <= 0 || x->P <= 0 || !fits_int(x->N) || !fits_int(x->T * x->P))
+        return REART_ERR_INVALID_ARG;
+    if (!x->cano || !x->w0 || !x->b0 || !x->w2 || !x->ysoft || !x->tau || !x->gW || !x->d6 || !x->tr || !x->gR || !x->gtr ||
+        !x->m_seg || !x->v_seg || !x->m_d6 || !x->v_d6 || !x->m_tr || !x->v_tr || !x->step || !x->partials || !x->tickets ||
+        !x->loss_local || !x->bucket || !x->loss_out || x->phase < 0 || x->phase > 2 || x->world < 1 || x->rank < 0 ||
+        x->rank >= x->world)
+        return REART_ERR_INVALID_ARG;
+    RelaxTail a = {};
+    a.cano = x->cano; a.w0 = x->w0; a.b0 = x->b0; a.w2 = x->w2; a.ysoft = x->ysoft; a.tau = x->tau; a.gW = x->gW;
+    a.d6 = x->d6; a.tr = x->tr; a.gR = x->gR; a.gtr = x->gtr;
+    a.m_seg = x->m_seg; a.v_seg = x->v_seg; a.m_d6 = x->m_d6; a.v_d6 = x->v_d6; a.m_tr = x->m_tr; a.v_tr = x->v_tr;
+    a.step = x->step; a.lr_pose = x->lr_pose; a.lr_seg = x->lr_seg; a.beta1 = x->beta1; a.beta2 = x->beta2; a.eps = x->eps;
+    a.wd = x->weight_decay; a.partials = x->partials; a.tickets = x->tickets; a.loss_local = x->loss_local;
+    a.bucket = x->bucket; a.loss_out = x->loss_out;
+    a.peer_base = reinterpret_cast<const unsigned long long*>(x->peer_base); a.epoch = x->epoch;
+    a.rank = x->rank; a.world = x->world; a.n_pad = x->n_pad; a.phase = x->phase;
+    a.N = (int)x->N; a.H = (int)x->H; a.P = (int)x->P; a.T = (int)x->T;
+    return launch_relax_tail(a, static_cast<cudaStream_t>(stream_));
 }
 
 int reart_rot6d_fwd(const float* d6, int64_t B, float* R, void* stream_) {

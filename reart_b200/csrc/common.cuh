@@ -142,31 +142,167 @@ __device__ __forceinline__ int rescan_chunk(const float* __restrict__ tpacked_b,
     return start;   // unreachable for finite inputs (the minimum was produced by this very arithmetic)
 }
 
-// Index recovery inside an x-SORTED chunk (skin_fwd_sorted_kernel): only points with |q.x - x| <= sqrt(dmin) can
-// reproduce dmin (d >= fl(dx*dx)), so binary-search that window (with a 1e-5 relative safety margin, the exact test
-// still decides) and take the LOWEST ORIGINAL offset among the exact matches -- the same answer as a linear scan of
-// the unsorted chunk.
-__device__ __forceinline__ int rescan_sorted_chunk(const float* __restrict__ packed_b, const unsigned char* __restrict__ perm_b,
-                                                   unsigned chunk, int chunk_pts, float qx, float qy, float qz, float dmin) {
-    const int base = (int)chunk * chunk_pts;
-    const float* __restrict__ gx = packed_b + (int64_t)(base >> 2) * kGroupFloats;      // x of sorted position k: gx[(k>>2)*12 + (k&3)]
+// ----------------------------------------------------------------------------- batched index recovery
+// The two re-scans above walk their candidates one dependent load at a time; at L2 latency that serial depth (8 probes
+// of a binary search + one iteration per window candidate, the slowest lane of a warp deciding) was the whole cost of
+// the energy column pass (profiles/r01_small_kernels_ncu.md: 10.5 of 32 lanes active, DRAM 3.9 %).  The batched forms
+// below issue their loads in independent groups, so a recovery is 2-4 memory round trips deep.
+
+// 32-target row chunk (chunk_pts == kChunk): the x lanes of two groups are fetched per round trip, y/z only for a
+// group that holds a candidate; returns at the first exact match in index order (same answer as rescan_chunk).  Few
+// registers on purpose: this pass lives on occupancy (every load is an L2 round trip).
+__device__ __forceinline__ int rescan_chunk32(const float* __restrict__ tpacked_b, unsigned chunk, float qx, float qy,
+                                              float qz, float dmin) {
+    const int start = (int)chunk * kChunk;
+    const float4* __restrict__ cg = reinterpret_cast<const float4*>(tpacked_b) + (start / 4) * 3;
+#pragma unroll 1
+    for (int h = 0; h < 4; ++h) {
+        const float4 X0 = __ldg(cg + 6 * h), X1 = __ldg(cg + 6 * h + 3);
+        const float a0 = __fsub_rn(qx, X0.x), a1 = __fsub_rn(qx, X0.y), a2 = __fsub_rn(qx, X0.z), a3 = __fsub_rn(qx, X0.w);
+        const float b0 = __fsub_rn(qx, X1.x), b1 = __fsub_rn(qx, X1.y), b2 = __fsub_rn(qx, X1.z), b3 = __fsub_rn(qx, X1.w);
+        const bool c0 = __fmul_rn(a0, a0) <= dmin, c1 = __fmul_rn(a1, a1) <= dmin, c2 = __fmul_rn(a2, a2) <= dmin, c3 = __fmul_rn(a3, a3) <= dmin;
+        const bool e0 = __fmul_rn(b0, b0) <= dmin, e1 = __fmul_rn(b1, b1) <= dmin, e2 = __fmul_rn(b2, b2) <= dmin, e3 = __fmul_rn(b3, b3) <= dmin;
+        const bool anyc = c0 | c1 | c2 | c3, anye = e0 | e1 | e2 | e3;
+        float4 Y0, Z0, Y1, Z1;
+        if (anyc) { Y0 = __ldg(cg + 6 * h + 1); Z0 = __ldg(cg + 6 * h + 2); }
+        if (anye) { Y1 = __ldg(cg + 6 * h + 4); Z1 = __ldg(cg + 6 * h + 5); }
+        if (anyc) {
+            if (c0 && sqdist_scalar(qx, qy, qz, X0.x, Y0.x, Z0.x) == dmin) return start + 8 * h;
+            if (c1 && sqdist_scalar(qx, qy, qz, X0.y, Y0.y, Z0.y) == dmin) return start + 8 * h + 1;
+            if (c2 && sqdist_scalar(qx, qy, qz, X0.z, Y0.z, Z0.z) == dmin) return start + 8 * h + 2;
+            if (c3 && sqdist_scalar(qx, qy, qz, X0.w, Y0.w, Z0.w) == dmin) return start + 8 * h + 3;
+        }
+        if (anye) {
+            if (e0 && sqdist_scalar(qx, qy, qz, X1.x, Y1.x, Z1.x) == dmin) return start + 8 * h + 4;
+            if (e1 && sqdist_scalar(qx, qy, qz, X1.y, Y1.y, Z1.y) == dmin) return start + 8 * h + 5;
+            if (e2 && sqdist_scalar(qx, qy, qz, X1.z, Y1.z, Z1.z) == dmin) return start + 8 * h + 6;
+            if (e3 && sqdist_scalar(qx, qy, qz, X1.w, Y1.w, Z1.w) == dmin) return start + 8 * h + 7;
+        }
+    }
+    return start;   // unreachable for finite inputs
+}
+
+// x-SORTED copy of a cloud, read ONLY by the index recovery (the search streams the other cloud and reads this one in
+// its original AoS order), so its layout is chosen for the recovery: per block of kSortedChunk = 256 points
+//     xs[256] | yz[256][2]          (3 * 256 floats = the same 12 B/point as any packed copy)
+// sorted ascending by x (+INF padding last), with perm[k] = original offset of the point at sorted position k and
+// a quantile index xq[16] = xs[15], xs[31], ..., xs[255].  A recovery probes the 64-byte quantile line, then the 16
+// contiguous x values of the segment (two 16-way probes instead of an 8-step binary search), then walks the window
+// eight x values (one 32-byte sector) per round trip and fetches (y,z) only for candidates.
+constexpr int kSortedChunk = 256;
+constexpr int kQuantiles = 16;
+constexpr int kSortedChunkFloats = 3 * kSortedChunk;
+
+__device__ __forceinline__ int count_below(const float4& v, float lo) {
+    return (v.x < lo ? 1 : 0) + (v.y < lo ? 1 : 0) + (v.z < lo ? 1 : 0) + (v.w < lo ? 1 : 0);
+}
+
+// One batch of the window walk: eight consecutive sorted positions k0 .. k0+7 (x values in X0, X1).  All candidate
+// (y,z) loads are issued together (predicated, independent), then tested -- one memory round trip per batch.
+__device__ __forceinline__ void sorted_batch_test(const float2* __restrict__ yz, const unsigned char* __restrict__ pm,
+                                                  int k0, const float4& X0, const float4& X1, float qx, float qy, float qz,
+                                                  float dmin, int& best) {
+    const float x[8] = {X0.x, X0.y, X0.z, X0.w, X1.x, X1.y, X1.z, X1.w};
+    bool c[8];
+    float2 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float d = __fsub_rn(qx, x[e]);
+        c[e] = __fmul_rn(d, d) <= dmin;                        // false for +INF padding and for everything outside the window
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        if (c[e]) v[e] = __ldg(yz + k0 + e);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        if (c[e] && sqdist_scalar(qx, qy, qz, x[e], v[e].x, v[e].y) == dmin) best = min(best, (int)pm[k0 + e]);
+}
+
+__device__ __forceinline__ int rescan_sorted_chunk_q(const float* __restrict__ sorted_b, const unsigned char* __restrict__ perm_b,
+                                                     const float* __restrict__ xq_b, unsigned chunk, float qx, float qy,
+                                                     float qz, float dmin) {
+    const int base = (int)chunk * kSortedChunk;
+    const float* __restrict__ blk = sorted_b + (int64_t)chunk * kSortedChunkFloats;
+    const float4* __restrict__ xs4 = reinterpret_cast<const float4*>(blk);                        // 64 float4 of x
+    const float2* __restrict__ yz = reinterpret_cast<const float2*>(blk + kSortedChunk);
+    const unsigned char* __restrict__ pm = perm_b + base;
     const float r = sqrtf(dmin) * 1.00001f + 1e-30f;
     const float lo = qx - r - fabsf(qx) * 1e-6f, hi = qx + r + fabsf(qx) * 1e-6f;
-    int a = 0, b = chunk_pts;                                                 // first position with x >= lo
-    while (a < b) {
-        const int m = (a + b) >> 1;
-        if (__ldg(gx + (m >> 2) * kGroupFloats + (m & 3)) < lo) a = m + 1; else b = m;
-    }
+    const float4* __restrict__ q4 = reinterpret_cast<const float4*>(xq_b + (int64_t)chunk * kQuantiles);
+    const float4 q0 = __ldg(q4), q1 = __ldg(q4 + 1), q2 = __ldg(q4 + 2), q3 = __ldg(q4 + 3);
+    int s = count_below(q0, lo) + count_below(q1, lo) + count_below(q2, lo) + count_below(q3, lo);
+    s = min(s, kQuantiles - 1);
+    const float4 a0 = __ldg(xs4 + 4 * s), a1 = __ldg(xs4 + 4 * s + 1), a2 = __ldg(xs4 + 4 * s + 2), a3 = __ldg(xs4 + 4 * s + 3);
+    const int a = 16 * s + count_below(a0, lo) + count_below(a1, lo) + count_below(a2, lo) + count_below(a3, lo);
     int best = 0x7fffffff;
-    for (int k = a; k < chunk_pts; ++k) {
-        const float* g = gx + (k >> 2) * kGroupFloats + (k & 3);
-        const float x = __ldg(g);
-        if (x > hi) break;
-        const float dx = __fsub_rn(qx, x);
-        if (__fmul_rn(dx, dx) <= dmin && sqdist_scalar(qx, qy, qz, x, __ldg(g + 4), __ldg(g + 8)) == dmin)
-            best = min(best, (int)perm_b[base + k]);
+    // window walk, two groups (8 positions) per step, the NEXT step's x values already in flight
+    const float4 inf4 = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+    constexpr int G = kSortedChunk / 4;
+    int g = (a >> 2) & ~1;                                     // even group: the pair (g, g+1) is always inside the block
+    float4 X0 = g < G ? __ldg(xs4 + g) : inf4, X1 = g < G ? __ldg(xs4 + g + 1) : inf4;
+#pragma unroll 1
+    while (g < G) {
+        const int gn = g + 2;
+        const float4 N0 = gn < G ? __ldg(xs4 + gn) : inf4, N1 = gn < G ? __ldg(xs4 + gn + 1) : inf4;
+        sorted_batch_test(yz, pm, 4 * g, X0, X1, qx, qy, qz, dmin, best);
+        if (X1.w > hi) break;                                  // sorted: nothing further can match
+        X0 = N0; X1 = N1; g = gn;
     }
     return base + (best == 0x7fffffff ? 0 : best);
+}
+
+// Writes one point of a sorted block (used by the two kernels that build the copy).
+__device__ __forceinline__ void sorted_block_store(float* __restrict__ sorted_b, int64_t chunk, int k, float x, float y, float z) {
+    float* blk = sorted_b + chunk * kSortedChunkFloats;
+    blk[k] = x;
+    reinterpret_cast<float2*>(blk + kSortedChunk)[k] = make_float2(y, z);
+}
+
+// ----------------------------------------------------------------------------- block sort for the x-sorted copies
+__device__ __forceinline__ unsigned orderable_bits(float v) {
+    const unsigned u = __float_as_uint(v);
+    return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+
+// Bitonic sort of one (x, offset) key per thread across a 256-thread block, ascending by thread index.  Exchange
+// distances below 32 stay inside a warp (register shuffles); only the 6 steps with distance >= 32 go through shared
+// memory (round 1 ran all 36 steps through shared memory with a barrier each: 62.8 us for 64 x 16k points).
+// The exchange buffer must NOT be __restrict__: with it nvcc treats every store but the last as dead (no same-thread
+// read in between) and deletes them across the barriers.
+__device__ __forceinline__ u64 block_bitonic_sort256(u64 key, volatile u64* xchg) {
+    const int i = threadIdx.x;
+#pragma unroll
+    for (int k = 2; k <= kSortedChunk; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            u64 other;
+            if (j >= 32) {
+                xchg[i] = key;
+                __syncthreads();
+                other = xchg[i ^ j];
+                __syncthreads();
+            } else {
+                other = __shfl_xor_sync(0xffffffffu, key, j);
+            }
+            const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+            key = keep_min ? (other < key ? other : key) : (other > key ? other : key);
+        }
+    }
+    return key;
+}
+
+
+// Fixed-point scale shared by the two energy passes: every reverse-direction gradient term is bounded by
+// |2 gscale| * D along an axis, D = sqrt(largest column minimum), and at most M of them meet in one accumulator,
+// so 2^k with k = 62 - ceil(log2(M |2 gscale| D)) keeps any sum inside an int64.  Integer addition is associative:
+// the scatter becomes independent of the order in which the atomics land.
+__device__ __forceinline__ int fixed_point_exponent(unsigned bound_bits, float g2abs, int M) {
+    const float D = sqrtf(__uint_as_float(bound_bits)) * 1.0001f;
+    const float maxsum = (float)M * g2abs * D;
+    if (!(maxsum > 0.f) || !(maxsum < 3.0e38f)) return 0;
+    int e;
+    frexpf(maxsum, &e);                                                            // maxsum < 2^e
+    return max(-100, min(100, 61 - e));
 }
 
 }  // namespace reart

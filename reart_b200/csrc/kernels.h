@@ -20,6 +20,7 @@ struct KnnDir {
     int keys_preset;              // 1: caller already set keys to 0xff.. (fused pipelines)
     int chunk_pts;                // targets per arg-min chunk recorded in the key (finalize re-scan span)
     const unsigned char* perm;    // null, or [B,nt_pad]: tpacked is x-sorted per chunk_pts block (perm = original offset)
+    const float* xq;              // with perm: [B, nt_pad/256, 16] quantile index of every sorted block (common.cuh)
 };
 
 struct KnnParams {
@@ -40,11 +41,13 @@ struct SymParams {
     int col_chunk_pts;            // filled by the launcher (32 * R / S)
     int keys_preset;
     int variant;                  // 0 = default; 1/2/4/8 = number of column sub-chunks per warp (tuning)
+    unsigned* col_bound;          // null, or one word (zero on entry): atomicMax of the finite column minima every CTA
+                                  // saw, as float bits -- an upper bound of every final column minimum (energy.cu)
 };
 
 int launch_pack_cloud(const float* pts, float* packed, int64_t B, int64_t P, cudaStream_t stream);
-int launch_pack_cloud_sorted(const float* pts, float* packed, unsigned char* perm, int64_t B, int64_t P, int64_t n_pad,
-                             cudaStream_t stream);
+int launch_pack_cloud_sorted(const float* pts, float* packed, unsigned char* perm, float* xq, int64_t B, int64_t P,
+                             int64_t n_pad, cudaStream_t stream);
 int launch_knn1_search(KnnParams& p, cudaStream_t stream);
 int launch_knn1_finalize(const KnnParams& p, cudaStream_t stream);
 int launch_chamfer_sym(SymParams& p, cudaStream_t stream);
@@ -59,10 +62,11 @@ int launch_chamfer_bidir_bwd(const float* src, const float* tgt, const int64_t* 
 int launch_skin_fwd(const float* cano, const float* W, const float* R, const float* tr, int64_t T, int64_t N, int64_t P,
                     float* out, float* out_packed, cudaStream_t stream);
 int launch_skin_fwd_sorted(const float* cano, const float* W, const float* R, const float* tr, int64_t T, int64_t N,
-                           int64_t P, float* out, float* out_packed, unsigned char* perm, int64_t n_pad,
+                           int64_t P, float* out, float* out_packed, unsigned char* perm, float* xq, int64_t n_pad,
                            cudaStream_t stream);
+int64_t skin_bwd_workspace_floats(int64_t T, int64_t N, int64_t P);
 int launch_skin_bwd(const float* cano, const float* W, const float* R, const float* tr, const float* g, int64_t T,
-                    int64_t N, int64_t P, float* gW, float* gR, float* gtr, cudaStream_t stream);
+                    int64_t N, int64_t P, float* gW, float* gR, float* gtr, float* partials, cudaStream_t stream);
 
 int launch_rot6d_fwd(const float* d6, int64_t B, float* R, cudaStream_t stream);
 int launch_rot6d_bwd(const float* d6, const float* gR, int64_t B, float* gd6, cudaStream_t stream);
@@ -93,17 +97,23 @@ struct EnergyParams {
     const float* tgt;             // [B,M,3] observed frames
     const float* src_packed;      // packed copies (re-scan)
     const float* tgt_packed;
-    const unsigned char* src_perm;      // [B,n_pad] or null: src_packed is x-sorted per col_chunk_pts block, perm = original offset
+    const unsigned char* src_perm;      // [B,n_pad]: src_packed is x-sorted per 256-point block, perm = original offset
+    const float* src_xq;                // [B,n_pad/256,16] quantile index of the sorted blocks
     const unsigned long long* keys_a;   // [B,N] row keys
     const unsigned long long* keys_b;   // [B,M] column keys
     int B, N, M, n_pad, m_pad;
     int row_chunk_pts, col_chunk_pts;
     float gscale;                 // upstream gradient of every per-point distance (1 for torch.sum)
-    float* g_src;                 // [B,N,3], overwritten (the row pass stores, the column pass adds)
-    double* loss;                 // [1], zero on entry: sum of all per-point distances
+    float* g_src;                 // [B,N,3], overwritten by the row pass
+    double* loss;                 // [1]: sum of all per-point distances (written, not accumulated)
+    long long* acc;               // [B,N,3] fixed-point accumulators of the reverse-direction terms, ZERO on entry
+    const unsigned* col_bound;    // [1] float bits >= every column minimum (SymParams::col_bound)
+    double* partials;             // [2 * energy_max_blocks()] per-block loss partials (no initialisation needed)
+    unsigned* ticket;             // [1] ZERO on entry
     float* d_fwd; int64_t* i_fwd; // optional [B,N]
     float* d_bwd; int64_t* i_bwd; // optional [B,M]
 };
+int energy_max_blocks();
 int launch_energy_bwd(const EnergyParams& p, cudaStream_t stream);
 
 int launch_knn(const float* ref, const float* query, int64_t B, int64_t n, int64_t m, int k, float* dist, int64_t* idx,
@@ -119,6 +129,34 @@ int launch_segmlp(const float* x, const float* w0, const float* b0, const float*
                   int64_t H, int64_t P, float* logits, float* gw0, float* gb0, float* gw2, cudaStream_t stream);
 int launch_gumbel_st(const float* logits, const float* expo, const float* tau, const float* gW, int64_t N, int64_t P,
                      float* W, float* ysoft, float* glogits, cudaStream_t stream);
+
+// Fused frame-independent head / tail of one relaxation iteration (relax.cu).
+int launch_relax_head(const float* cano, const float* w0, const float* b0, const float* w2, const float* expo,
+                      const float* tau, const float* d6, int64_t N, int64_t H, int64_t P, int64_t T, float* logits,
+                      float* W, float* ysoft, float* R, cudaStream_t stream);
+struct RelaxTail {
+    const float* cano;            // [N,3]
+    float* w0; float* b0; float* w2;              // seg MLP parameters [H,3], [H], [P,H] -- updated in place
+    const float* ysoft;           // [N,P] soft assignment saved by the head
+    const float* tau;             // [1]
+    const float* gW;              // [N,P]  d loss / d W
+    float* d6; float* tr;         // [T,P,6], [T,P,3] pose parameters -- updated in place
+    const float* gR; const float* gtr;            // [T,P,9], [T,P,3]
+    float* m_seg; float* v_seg;   // [4H + PH] Adam moments of [w0 | b0 | w2]
+    float* m_d6; float* v_d6; float* m_tr; float* v_tr;
+    float* step;                  // [1] completed optimisation steps (advanced by the kernel)
+    float lr_pose, lr_seg, beta1, beta2, eps, wd;
+    float* partials;              // [ceil(N/128)][4H + PH] per-chunk seg-gradient partials
+    unsigned* tickets;            // [2] zero before the FIRST call; the kernel re-arms them itself
+    const double* loss_local;     // [1] this rank's loss
+    float* bucket;                // [4H + PH + 1] reduced seg gradients + loss
+    float* loss_out;              // [1] all-rank loss of the step
+    const unsigned long long* peer_base; unsigned* epoch; int rank, world, n_pad;   // one-shot all-reduce (world > 1)
+    int phase;                    // 0 everything; 1 gradients -> bucket only; 2 Adam from an (externally reduced) bucket
+    int N, H, P, T;
+};
+int64_t relax_tail_workspace_floats(int64_t N, int64_t H, int64_t P);
+int launch_relax_tail(const RelaxTail& a, cudaStream_t stream);
 
 int launch_allreduce_oneshot(const unsigned long long* peer_base, int rank, int world, int64_t n, int64_t n_pad,
                              unsigned* epoch, float* data, cudaStream_t stream);

@@ -67,38 +67,27 @@ int launch_pack_cloud(const float* pts, float* packed, int64_t B, int64_t P, cud
 // perm [B,n_pad] = original offset inside the block of the point now at each sorted position (see skin.cu
 // skin_fwd_sorted_kernel, which does the same for the skinned cloud).  n_pad is a multiple of 256.
 __global__ void __launch_bounds__(256) pack_cloud_sorted_kernel(const float* __restrict__ pts, float* __restrict__ packed,
-                                                                unsigned char* __restrict__ perm, int P, int n_pad) {
-    __shared__ u64 keys[256];
+                                                                unsigned char* __restrict__ perm, float* __restrict__ xq,
+                                                                int P, int n_pad) {
+    __shared__ u64 xchg[256];
     __shared__ float sx[3 * 256];
     const int b = blockIdx.y, i = threadIdx.x, base = blockIdx.x * 256, n = base + i;
     float x = INFINITY, y = INFINITY, z = INFINITY;
     if (n < P) { const float* s = pts + ((int64_t)b * P + n) * 3; x = s[0]; y = s[1]; z = s[2]; }
     sx[i] = x; sx[256 + i] = y; sx[512 + i] = z;
-    const unsigned u = __float_as_uint(x);
-    keys[i] = ((u64)(u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u)) << 32) | (u64)i;
-    __syncthreads();
-    for (int k = 2; k <= 256; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const int ixj = i ^ j;
-            if (ixj > i) {
-                const u64 a = keys[i], c = keys[ixj];
-                if ((a > c) == ((i & k) == 0)) { keys[i] = c; keys[ixj] = a; }
-            }
-            __syncthreads();
-        }
-    }
-    const int src = (int)(keys[i] & 0xffu);
-    float* g = packed + (int64_t)b * n_pad * 3 + (int64_t)(n >> 2) * kGroupFloats + (i & 3);
-    g[0] = sx[src]; g[4] = sx[256 + src]; g[8] = sx[512 + src];
+    const u64 key = block_bitonic_sort256(((u64)orderable_bits(x) << 32) | (u64)i, xchg);
+    const int src = (int)(key & 0xffu);
+    sorted_block_store(packed + (int64_t)b * n_pad * 3, blockIdx.x, i, sx[src], sx[256 + src], sx[512 + src]);
     perm[(int64_t)b * n_pad + n] = (unsigned char)src;
+    if ((i & 15) == 15) xq[((int64_t)b * (n_pad / 256) + blockIdx.x) * kQuantiles + (i >> 4)] = sx[src];
 }
 
-int launch_pack_cloud_sorted(const float* pts, float* packed, unsigned char* perm, int64_t B, int64_t P, int64_t n_pad,
-                             cudaStream_t stream) {
+int launch_pack_cloud_sorted(const float* pts, float* packed, unsigned char* perm, float* xq, int64_t B, int64_t P,
+                             int64_t n_pad, cudaStream_t stream) {
     if (B <= 0) return kOk;
     if (n_pad % 256 != 0 || n_pad < P || B > 65535) return kErrUnsupported;
     dim3 grid((unsigned)(n_pad / 256), (unsigned)B);
-    pack_cloud_sorted_kernel<<<grid, 256, 0, stream>>>(pts, packed, perm, (int)P, (int)n_pad);
+    pack_cloud_sorted_kernel<<<grid, 256, 0, stream>>>(pts, packed, perm, xq, (int)P, (int)n_pad);
     REART_CHECK_LAUNCH();
     return kOk;
 }
@@ -223,9 +212,15 @@ __global__ void knn1_finalize_kernel(const KnnParams p, int dir_only) {
             const float dmin = __uint_as_float((unsigned)(key >> 32));
             const unsigned chunk = (unsigned)(key & 0xffffffffu);
             const float* qp = D.q + e * 3;
-            int j = D.perm ? rescan_sorted_chunk(D.tpacked + b * (int64_t)D.nt_pad * 3, D.perm + b * (int64_t)D.nt_pad, chunk,
-                                                 D.chunk_pts, qp[0], qp[1], qp[2], dmin)
-                           : rescan_chunk(D.tpacked + b * (int64_t)D.nt_pad * 3, chunk, D.chunk_pts, D.nt_pad, qp[0], qp[1], qp[2], dmin);
+            int j;
+            if (D.perm)
+                j = rescan_sorted_chunk_q(D.tpacked + b * (int64_t)D.nt_pad * 3, D.perm + b * (int64_t)D.nt_pad,
+                                          D.xq + b * (int64_t)(D.nt_pad / kSortedChunk) * kQuantiles, chunk, qp[0], qp[1],
+                                          qp[2], dmin);
+            else if (D.chunk_pts == kChunk)
+                j = rescan_chunk32(D.tpacked + b * (int64_t)D.nt_pad * 3, chunk, qp[0], qp[1], qp[2], dmin);
+            else
+                j = rescan_chunk(D.tpacked + b * (int64_t)D.nt_pad * 3, chunk, D.chunk_pts, D.nt_pad, qp[0], qp[1], qp[2], dmin);
             if (j >= D.nt) j = 0;
             if (D.out_dists) D.out_dists[e] = dmin;
             if (D.out_idx) D.out_idx[e] = (int64_t)j;

@@ -32,6 +32,8 @@ class _EngineBase:
 
     # subclasses: _iteration() -> loss tensor (local part), self.optimizer, self.bucket
     def _run_iteration(self):
+        if getattr(self, "native", False):
+            return self._run_iteration_native()
         if getattr(self, "sink", None) is not None:
             return self._run_iteration_sink()
         # set_to_none: AccumulateGrad then adopts the fresh gradient tensors (no zero-fill and no add kernels); inside a
@@ -59,11 +61,20 @@ class _EngineBase:
         self.optimizer.step()
         return total
 
+    def _opt_params(self):
+        return [p for g in self.optimizer.param_groups for p in g["params"]]
+
+    def _reset_optimizer_state(self):
+        for st in self.optimizer.state.values():
+            for v in st.values():
+                if torch.is_tensor(v):
+                    v.zero_()                                  # step, exp_avg, exp_avg_sq (kept in place)
+
     def _capture(self):
         """Warm up (allocator, library handles, NCCL communicator, lazily created Adam state), capture one
         iteration, then put parameters, optimiser state and the RNG stream back where they were, so a graph
         run is step-for-step the same optimisation as an eager run."""
-        params = [p for g in self.optimizer.param_groups for p in g["params"]]
+        params = self._opt_params()
         snapshot = [p.detach().clone() for p in params]
         dev = params[0].device
         rng_state = torch.cuda.get_rng_state(dev)
@@ -82,10 +93,7 @@ class _EngineBase:
         with torch.no_grad():
             for p, q in zip(params, snapshot):
                 p.copy_(q)
-            for st in self.optimizer.state.values():
-                for v in st.values():
-                    if torch.is_tensor(v):
-                        v.zero_()                              # step, exp_avg, exp_avg_sq (kept in place)
+            self._reset_optimizer_state()
         torch.cuda.set_rng_state(rng_state, dev)
         torch.cuda.synchronize()
 
@@ -114,7 +122,8 @@ class RelaxationEngine(_EngineBase):
 
     def __init__(self, cano: torch.Tensor, frames: torch.Tensor, num_parts: int, ctx: Optional[DistContext] = None,
                  trans_lr: float = 1e-2, seg_lr: float = 1e-3, weight_decay: float = 0.0, use_graph: bool = True,
-                 seed: int = 2, flow_ref=None, cano_idx: int = 0, lambda_flow: float = 1.0, robust_flow: bool = False):
+                 seed: int = 2, flow_ref=None, cano_idx: int = 0, lambda_flow: float = 1.0, robust_flow: bool = False,
+                 native: Optional[bool] = None, betas=(0.9, 0.999), eps: float = 1e-8):
         """flow_ref: optional ``flow_utils.FlowReference`` (run_robot.py:78-84) enabling the flow loss of
         run_robot.py:194-213.  Consecutive frames couple across shard boundaries: under frame sharding each rank
         receives one skinned frame per iteration from the previous rank (``dist.halo_from_previous_rank``)."""
@@ -143,6 +152,114 @@ class RelaxationEngine(_EngineBase):
         self.sink = ops.GradSink(H, num_parts, dev, extra_scalars=1, reducer=reducer)
         self.model.seg_head.grad_sink = self.sink
         self.pairs_per_step_local = 2 * (hi - lo) * self.cano.shape[0] * self.frames.shape[1]
+        # recon-only iterations run on the fused head / energy / tail kernels with the library's own Adam (8 launches per
+        # step, no autograd); extra losses on the skinned cloud (flow) keep the autograd composition
+        self.native = (flow_ref is None) if native is None else bool(native)
+        if self.native:
+            if flow_ref is not None:
+                raise ValueError("the native fused iteration covers the recon loss only; pass native=False with a flow loss")
+            self._init_native(trans_lr, seg_lr, weight_decay, betas, eps)
+
+    # ------------------------------------------------------------------------------------------ native fused iteration
+    def _init_native(self, trans_lr, seg_lr, weight_decay, betas, eps):
+        import ctypes
+        from . import _lib
+        L = _lib.lib()
+        dev = self.cano.device
+        m = self.model
+        T, P = m.proposal_6d.shape[0], m.num_parts
+        N, M = self.cano.shape[0], self.frames.shape[1]
+        conv0, conv2 = m.seg_head.model[0], m.seg_head.model[2]
+        H = conv0.weight.shape[0]
+        nseg = 4 * H + P * H
+        f32 = dict(dtype=torch.float32, device=dev)
+        b = self._nat = {}
+        b["expo"] = torch.empty(N, P, **f32)
+        b["W"], b["ysoft"] = torch.empty(N, P, **f32), torch.empty(N, P, **f32)
+        b["R"] = torch.empty(T, P, 3, 3, **f32)
+        b["skinned"] = torch.empty(T, N, 3, **f32)
+        b["loss64"] = torch.zeros(1, dtype=torch.float64, device=dev)
+        b["gW"] = torch.empty(N, P, **f32)
+        b["gpose"] = torch.empty(T * P * 12, **f32)
+        b["gR"], b["gtr"] = b["gpose"][:T * P * 9], b["gpose"][T * P * 9:]
+        b["ws_bytes"] = int(L.reart_energy_workspace_bytes(T, N, M))
+        b["ws"] = _lib.workspace(b["ws_bytes"], dev)
+        b["tail_ws"] = _lib.workspace(int(L.reart_relax_tail_workspace_bytes(N, H, P)), dev)
+        for k, ref in (("seg", None), ("d6", m.proposal_6d), ("tr", m.proposal_t)):
+            shape = (nseg,) if ref is None else tuple(ref.shape)
+            b["m_" + k], b["v_" + k] = torch.zeros(shape, **f32), torch.zeros(shape, **f32)
+        b["step"] = torch.zeros(1, **f32)
+        b["tickets"] = torch.zeros(2, dtype=torch.int32, device=dev)
+        b["bucket"] = torch.zeros(nseg + 1, **f32)
+        b["loss_out"] = torch.zeros(1, **f32)
+        b["dims"] = (T, N, M, P, H)
+        red = self.sink.reducer if self.sink is not None else None
+        self.model.seg_head.grad_sink = None                     # the autograd sink is not used on this path
+        oneshot = red if (red is not None and hasattr(red, "peer_base")) else None
+        b["nccl"] = red is not None and oneshot is None
+        a = _lib.RelaxTailArgs()
+        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        a.cano, a.w0, a.b0, a.w2 = p(self.cano), p(conv0.weight), p(conv0.bias), p(conv2.weight)
+        a.ysoft, a.tau, a.gW = p(b["ysoft"]), p(self.tau), p(b["gW"])
+        a.d6, a.tr, a.gR, a.gtr = p(m.proposal_6d), p(m.proposal_t), p(b["gR"]), p(b["gtr"])
+        a.m_seg, a.v_seg, a.m_d6, a.v_d6, a.m_tr, a.v_tr = (p(b[k]) for k in ("m_seg", "v_seg", "m_d6", "v_d6", "m_tr", "v_tr"))
+        a.step = p(b["step"])
+        a.lr_pose, a.lr_seg, a.beta1, a.beta2, a.eps, a.weight_decay = trans_lr, seg_lr, betas[0], betas[1], eps, weight_decay
+        a.partials, a.tickets, a.loss_local = p(b["tail_ws"]), p(b["tickets"]), p(b["loss64"])
+        a.bucket, a.loss_out = p(b["bucket"]), p(b["loss_out"])
+        a.rank, a.world = (self.ctx.rank, self.ctx.world_size) if oneshot is not None else (0, 1)
+        if oneshot is not None:
+            assert oneshot.n == nseg + 1
+            a.peer_base, a.epoch, a.n_pad = p(oneshot.peer_base), p(oneshot.epoch), oneshot.n_pad
+        a.phase = 0
+        a.N, a.H, a.P, a.T = N, H, P, T
+        b["args"] = a
+        b["keep"] = (conv0, conv2, oneshot)
+        assert self.tau.dtype == torch.float32 and conv0.weight.is_contiguous() and conv2.weight.is_contiguous()
+
+    def _opt_params(self):
+        if self.native:
+            m = self.model
+            return [m.proposal_6d, m.proposal_t] + [q for q in m.seg_head.parameters() if q.requires_grad]
+        return super()._opt_params()
+
+    def _reset_optimizer_state(self):
+        if self.native:
+            for k in ("m_seg", "v_seg", "m_d6", "v_d6", "m_tr", "v_tr", "step"):
+                self._nat[k].zero_()
+            return
+        super()._reset_optimizer_state()
+
+    def _run_iteration_native(self):
+        """head -> [memset, skin (x-sorted copy), search, energy columns, energy rows, skin backward, reduce] -> tail."""
+        import ctypes
+        from . import _lib
+        from ._lib import check, ptr, stream_ptr
+        L = _lib.lib()
+        b = self._nat
+        T, N, M, P, H = b["dims"]
+        m = self.model
+        conv0, conv2 = m.seg_head.model[0], m.seg_head.model[2]
+        b["expo"].exponential_()                                  # the same RNG draw F.gumbel_softmax makes
+        with torch.cuda.device(self.cano.device):
+            check(L.reart_relax_head(ptr(self.cano), ptr(conv0.weight), ptr(conv0.bias), ptr(conv2.weight), ptr(b["expo"]),
+                                     ptr(self.tau), ptr(m.proposal_6d), N, H, P, T, None, ptr(b["W"]), ptr(b["ysoft"]),
+                                     ptr(b["R"]), stream_ptr()), "reart_relax_head")
+            check(L.reart_skinned_chamfer_fwd_bwd(ptr(self.cano), ptr(b["W"]), ptr(b["R"]), ptr(m.proposal_t), ptr(self.frames),
+                                                  ptr(self.frames_packed), T, N, M, P, ptr(b["skinned"]), ptr(b["loss64"]),
+                                                  ptr(b["gW"]), ptr(b["gR"]), ptr(b["gtr"]), None, 1, ptr(b["ws"]),
+                                                  b["ws_bytes"], stream_ptr()), "reart_skinned_chamfer_fwd_bwd")
+            a = b["args"]
+            if not b["nccl"]:
+                check(L.reart_relax_tail(ctypes.byref(a), stream_ptr()), "reart_relax_tail")
+            else:                                                 # no peer memory: gradients -> bucket, NCCL, Adam
+                a.phase = 1
+                check(L.reart_relax_tail(ctypes.byref(a), stream_ptr()), "reart_relax_tail")
+                self.ctx.all_reduce_sum_(b["bucket"])
+                a.phase = 2
+                check(L.reart_relax_tail(ctypes.byref(a), stream_ptr()), "reart_relax_tail")
+        self.skinned = b["skinned"]
+        return b["loss_out"][0]
 
     def _iteration(self):
         seg, weight = self.model.weights(self.cano, tau=self.tau)

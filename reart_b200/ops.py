@@ -62,9 +62,11 @@ class _Skin(Function):
         gW = torch.empty_like(W)
         gR = torch.empty_like(R)
         gtr = torch.empty_like(tr)
+        nbytes = L.reart_skin_bwd_workspace_bytes(T, N, P)
+        ws = _lib.workspace(nbytes, cano.device)
         with torch.cuda.device(cano.device):
             check(L.reart_skin_bwd(ptr(cano), ptr(W), ptr(R), ptr(tr), ptr(g), T, N, P, ptr(gW), ptr(gR), ptr(gtr),
-                                   stream_ptr()), "reart_skin_bwd")
+                                   ptr(ws), nbytes, stream_ptr()), "reart_skin_bwd")
         gW_out = gW if ctx.needs_input_grad[1] and ctx.w_dtype.is_floating_point else None
         return None, gW_out, gR, gtr
 
@@ -406,9 +408,11 @@ class _SkinnedChamfer(Function):
             N = cano.shape[0]
             g = _f32c(g_skinned)
             eW, eR, et = torch.empty_like(W), torch.empty_like(R), torch.empty_like(tr)
+            nbytes = L.reart_skin_bwd_workspace_bytes(T, N, P)
+            ws = _lib.workspace(nbytes, cano.device)
             with torch.cuda.device(cano.device):
                 check(L.reart_skin_bwd(ptr(cano), ptr(W), ptr(R), ptr(tr), ptr(g), T, N, P, ptr(eW), ptr(eR), ptr(et),
-                                       stream_ptr()), "reart_skin_bwd")
+                                       ptr(ws), nbytes, stream_ptr()), "reart_skin_bwd")
             gW, gR, gtr = gW + eW, gR + eR, gtr + et
         return (None, gW if ctx.w_float else None, gR, gtr, None, None, None)
 

@@ -42,10 +42,11 @@ timeit("Chamfer backward, both directions (`reart_chamfer_bidir_bwd`)", lambda: 
 timeit("skinning forward (`reart_skin_fwd`)", lambda: ops.skin(cano, W, R, tr), 12.0 * N + 4.0 * N * P + 48.0 * T * P + 12.0 * T * N, "GB/s", "reads 12N+4NP+48TP, writes 12TN")
 g = torch.randn(T, N, 3, device=dev)
 Wg, Rg, tg = W.clone().requires_grad_(True), R.clone().requires_grad_(True), tr.clone().requires_grad_(True)
+nb_ws = L.reart_skin_bwd_workspace_bytes(T, N, P); bws = torch.empty(nb_ws, dtype=torch.uint8, device=dev)
+gW_, gR_, gtr_ = torch.empty_like(W), torch.empty_like(R), torch.empty_like(tr)
 def skin_bwd():
-    gW, gR, gtr = torch.empty_like(W), torch.empty_like(R), torch.empty_like(tr)
-    _lib.check(L.reart_skin_bwd(_lib.ptr(cano), _lib.ptr(W), _lib.ptr(R), _lib.ptr(tr), _lib.ptr(g), T, N, P, _lib.ptr(gW), _lib.ptr(gR), _lib.ptr(gtr), _lib.stream_ptr()), "sb")
-timeit("skinning backward (`reart_skin_bwd`, two kernels)", skin_bwd, 12.0 * T * N * 2 + 12.0 * N + 4.0 * N * P * 2 + 48.0 * T * P * 2, "GB/s", "g is read by both kernels")
+    _lib.check(L.reart_skin_bwd(_lib.ptr(cano), _lib.ptr(W), _lib.ptr(R), _lib.ptr(tr), _lib.ptr(g), T, N, P, _lib.ptr(gW_), _lib.ptr(gR_), _lib.ptr(gtr_), _lib.ptr(bws), nb_ws, _lib.stream_ptr()), "sb")
+timeit("skinning backward (`reart_skin_bwd`: fused pass + fixed-order reduce)", skin_bwd, 12.0 * T * N + 12.0 * N + 4.0 * N * P * 2 + 48.0 * T * P * 2, "GB/s", "g read once; deterministic")
 def fused():
     Wt, Rt, tt = W.clone().requires_grad_(True), R.clone().requires_grad_(True), tr.clone().requires_grad_(True)
     loss, _ = ops.skinned_chamfer_loss(cano, Wt, Rt, tt, frames, packed, unit_grad=True)
