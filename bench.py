@@ -27,14 +27,16 @@ if ROOT not in sys.path:
 WORKLOADS = {
     # name: (T frames, N = M points, P parts) -- BASELINE.json configs
     "cfg3_16k": (64, 16384, 15),      # the sequence the north_star quotes its targets on (default)
-    "cfg2": (16, 4096, 15),           # nao-shaped relaxation model
+    "cfg2": (16, 4096, 15),           # nao-shaped relaxation model, recon + flow + assign losses
     "cfg3_4k": (64, 4096, 15),
     "cfg3_64k": (64, 65536, 15),
+    "cfg3_256k": (64, 262144, 15),
     "cfg4": (32, 16384, 8),           # sapien-shaped kinematic projection model (KinematicEngine)
-    "cfg5": (64, 32768, 15),
+    "cfg5": (64, 32768, 15),          # real-scan-shaped sequence; one cano_idx candidate fit per GPU
     "cfg3_16k_8f": (8, 16384, 15),    # one rank's shard of cfg3_16k at 8 GPUs (tuning aid)
     "tiny": (8, 2048, 6),
 }
+SWEEP = ("cfg2", "cfg3_4k", "cfg3_64k", "cfg3_256k", "cfg4", "cfg5")
 METRIC = "skinned_chamfer_fwd_bwd_directed_point_pairs_per_s"
 UNIT = "pairs/s"
 FLOP_PER_PAIR = 8.0                   # 3 FSUB + 1 FMUL + 2 FFMA
@@ -50,6 +52,8 @@ def parse_args():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the per-config sweep (N=1) / candidate fits (N>1)")
+    ap.add_argument("--sustained-s", type=float, default=10.0, help="seconds of back-to-back steps after the timed region (0: skip)")
     return ap.parse_args()
 
 
@@ -217,6 +221,249 @@ class ClockSampler:
         return out
 
 
+# ------------------------------------------------------------------------------------------------ GPU arm helpers
+def reference_python_cpu_baseline(T, N, P, budget_frames=4, iters=2):
+    """The reference's OWN Python path (networks/model.py BaseModel + networks/loss.py recon_loss over utils/chamfer.py,
+    with the torch stand-in for the absent chamferdist._C, oracle/ref_harness.py) on the host cores, when a staged copy
+    of the reference exists (baseline/_ref/reart, scripts/stage_reference.py).  Bounded sample: `budget_frames` frames of
+    the workload, `iters` optimisation iterations (fwd + bwd + Adam).  Returns None when the reference is not staged."""
+    staged = os.path.join(ROOT, "baseline", "_ref", "reart")
+    if not os.path.isdir(os.path.join(staged, "utils")):
+        return None
+    import torch
+    os.environ["REART_REFERENCE_ROOT"] = staged
+    from oracle import ref_harness
+    ref_harness.REFERENCE_ROOT = staged
+    ref = ref_harness.import_reference()
+    from reart_b200.synth import make_sequence
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Ts = min(T, budget_frames)
+    seq = make_sequence(T=Ts, N=N, P=P, seed=2)
+    cano = torch.from_numpy(seq["cano"]); frames = torch.from_numpy(seq["frames"])
+    torch.manual_seed(2)
+    model = ref.model.BaseModel(num_parts=P, pose_len=Ts)
+    cd = ref.chamfer.ChamferDistance()
+    seg_params = [q for q in model.seg_head.parameters() if q.requires_grad]
+    opt = torch.optim.Adam([{"params": [model.proposal_6d, model.proposal_t], "lr": 1e-2},
+                            {"params": seg_params, "lr": 1e-3}], lr=1e-3)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        pc_trans, _, _ = model(cano, tau=5.0)
+        loss = ref.loss.recon_loss(pc_trans, frames, chamfer_dist=cd)
+        opt.zero_grad(); loss.backward(); opt.step()
+    dt = (time.perf_counter() - t0) / iters
+    pairs = 2.0 * Ts * N * N
+    return {"value": pairs / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+            "iters_per_s_sample": 1.0 / dt, "iters_per_s_full_T": (pairs / dt) / (2.0 * T * N * N),
+            "sample": f"reference Python loop (BaseModel.forward + recon_loss + backward + Adam, torch stand-in for chamferdist._C), "
+                      f"{Ts} of {T} frames x {N}x{N} points, {iters} iterations, {dt:.2f} s/iteration"}
+
+
+def kernels_of_one_step(engine):
+    """Names and counts of the CUDA kernels ONE eager iteration launches (torch profiler / CUPTI); `ours` = those in
+    namespace reart.  Returns (ours_count, {name: count}) or (None, {}) when the profiler is unavailable."""
+    import torch
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            engine._run_iteration()
+            torch.cuda.synchronize()
+        names = {}
+        for ev in prof.events():
+            if getattr(ev, "device_type", None) is not None and "cuda" in str(ev.device_type).lower():
+                n = ev.name.split("(")[0].strip()
+                if n.lower().startswith("memcpy") or n.lower().startswith("memset"):
+                    continue
+                names[n] = names.get(n, 0) + 1
+        ours = sum(c for n, c in names.items() if "reart::" in n)
+        return (ours if names else None), names
+    except Exception:
+        return None, {}
+
+
+def make_engine(workload, ctx, dev, use_graph, scaling, extra_losses=True):
+    """Synthetic sequence + engine of one named workload.  Returns (engine, host cano, host frames, T_total, N, P, desc)."""
+    import numpy as np
+    import torch
+    from reart_b200.engine import KinematicEngine, RelaxationEngine
+    from reart_b200.synth import kinematic_init, make_flow_reference, make_sequence
+    T, N, P = WORKLOADS[workload]
+    T_total = T if scaling == "strong" else T * ctx.world_size
+    seq = make_sequence(T=T_total, N=N, P=P, seed=2)
+    cano_h = torch.from_numpy(seq["cano"]).pin_memory()
+    frames_h = torch.from_numpy(seq["frames"]).pin_memory()
+    desc = "relaxation model (base), recon loss"
+    if workload == "cfg4":
+        kw = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in kinematic_init(seq).items()}
+        engine = KinematicEngine(kw, torch.from_numpy(seq["part"]), cano_h.to(dev), frames_h.to(dev), ctx=ctx, use_graph=use_graph)
+        desc = "kinematic projection model, recon loss"
+    elif workload == "cfg2" and extra_losses:
+        refs, flows = make_flow_reference(seq, cano_idx=0, n_ref=N // 4)
+        from reart_b200.flow_utils import FlowReference
+        fr = FlowReference([torch.from_numpy(r).to(dev) for r in refs], [torch.from_numpy(f).to(dev) for f in flows])
+        kwargs = {}
+        try:
+            import inspect
+            if "assign" in inspect.signature(RelaxationEngine.__init__).parameters:
+                kwargs["assign"] = dict(downsample=4, assign_gap=5, lambda_assign=0.3)
+                desc = "relaxation model (base), recon + flow + assign losses"
+            else:
+                desc = "relaxation model (base), recon + flow losses"
+        except Exception:
+            pass
+        engine = RelaxationEngine(cano_h.to(dev), frames_h.to(dev), num_parts=P, ctx=ctx, use_graph=use_graph, flow_ref=fr,
+                                  cano_idx=0, **kwargs)
+    else:
+        engine = RelaxationEngine(cano_h.to(dev), frames_h.to(dev), num_parts=P, ctx=ctx, use_graph=use_graph)
+    return engine, cano_h, frames_h, T_total, N, P, desc
+
+
+def time_engine_steps(engine, ctx, K, W, flush, n_iter=15000, sampler=None):
+    """W untimed + K timed steps, each bracketed by its own CUDA events on the launch stream, L2 flushed in between
+    (untimed), max over ranks.  Returns (ms_per_step, wall_s, last loss tensor)."""
+    import torch
+    from reart_b200.engine import tau_schedule
+    dev = flush.device
+    for i in range(W):
+        engine.step(tau_schedule(i, n_iter, 5.0, 1.0))
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    ctx.barrier(); torch.cuda.synchronize()
+    if sampler:
+        sampler.begin()
+    t0 = time.perf_counter()
+    loss = None
+    for i in range(K):
+        flush.fill_(i & 0xff)
+        engine.tau.fill_(tau_schedule(W + i, n_iter, 5.0, 1.0))
+        ev[i][0].record()
+        loss = engine.step()
+        ev[i][1].record()
+    torch.cuda.synchronize(); ctx.barrier()
+    wall = time.perf_counter() - t0
+    if sampler:
+        sampler.end()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    ctx.all_reduce_max_(tmax)
+    return float(tmax.item()) / K, wall, loss
+
+
+def search_kernel_timing(engine, flush, reps=5):
+    """The dominant kernel (chamfer_sym_kernel) alone on this rank's shard: CUDA events on the launch stream, L2 flushed."""
+    import torch
+    from reart_b200 import _lib
+    L = _lib.lib()
+    dev = flush.device
+    Tl, N = engine.frames.shape[0], engine.cano.shape[0]
+    M = engine.frames.shape[1]
+    keys_a = torch.empty(Tl * N, dtype=torch.int64, device=dev); keys_b = torch.empty(Tl * M, dtype=torch.int64, device=dev)
+    skinned = engine.skinned.detach().contiguous()
+
+    def search():
+        _lib.check(L.reart_chamfer_sym_search(_lib.ptr(skinned), _lib.ptr(engine.frames_packed), Tl, N, M,
+                                              _lib.ptr(keys_a), _lib.ptr(keys_b), None, 0, _lib.stream_ptr()), "search")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        search()
+    k_ms = 0.0
+    for i in range(reps):
+        flush.fill_(i)
+        e0.record(); search(); e1.record(); torch.cuda.synchronize()
+        k_ms += e0.elapsed_time(e1)
+    return k_ms / reps, 2.0 * Tl * N * M, Tl * (12.0 * (N + M) + 8.0 * (N + M))
+
+
+def fp32_peak_tf(dev):
+    import torch
+    props = torch.cuda.get_device_properties(dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+    return props.multi_processor_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12, sm_max_mhz, props.multi_processor_count, peaks
+
+
+def sustained_run(engine, ctx, seconds, ms_per_step_hint, gpu_index, uuid, pairs_per_step, kernel_share, peak_tf, sm_max_mhz):
+    """>= `seconds` of back-to-back steps (graph replays, no flush, no host sync inside): what a real 15 000-iteration fit
+    sees.  SM clock / power / throttle reasons are sampled during the run (NVML)."""
+    import torch
+    n = max(50, int(seconds * 1e3 / max(ms_per_step_hint, 1e-3)))
+    sampler = ClockSampler(gpu_index, uuid) if ctx.is_main else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.barrier(); torch.cuda.synchronize()
+    if sampler:
+        sampler.begin()
+    e0.record()
+    for _ in range(n):
+        engine.step()
+    e1.record(); torch.cuda.synchronize(); ctx.barrier()
+    if sampler:
+        sampler.end()
+    clocks = sampler.stop() if sampler else None
+    ms = torch.tensor([e0.elapsed_time(e1) / n], dtype=torch.float64, device=engine.cano.device)
+    ctx.all_reduce_max_(ms)
+    ms = float(ms.item())
+    out = {"seconds": ms * n * 1e-3, "steps": n, "ms_per_step": ms, "value": pairs_per_step / (ms * 1e-3), "unit": UNIT,
+           "clocks": clocks, "l2": "no flush between steps (steady state of a fit)"}
+    if clocks and clocks.get("sm_mhz"):
+        # the step as a whole against the FP32 roofline: all pairs of the step / step time (not the kernel alone)
+        tf = FLOP_PER_PAIR * pairs_per_step / ctx.world_size / (ms * 1e-3) / 1e12
+        out["step_tflops_per_gpu"] = tf
+        out["step_frac_of_peak_at_max_clock"] = tf / peak_tf
+        out["step_frac_of_peak_at_observed_clock"] = tf / (peak_tf * clocks["sm_mhz"] / sm_max_mhz)
+        out["search_kernel_share_of_step_measured_cold"] = kernel_share
+    return out
+
+
+def sweep_entry(workload, ctx, dev, flush, steps, warmup, peak_tf):
+    import torch
+    engine, _, _, T_total, N, P, desc = make_engine(workload, ctx, dev, True, "strong")
+    ms, _, loss = time_engine_steps(engine, ctx, steps, warmup, flush)
+    k_ms, local_pairs, _ = search_kernel_timing(engine, flush, reps=3)
+    n_ours, names = kernels_of_one_step(engine)
+    pairs = 2.0 * T_total * N * N
+    ent = {"workload": workload, "what": desc, "T": T_total, "N": N, "P": P, "steps": steps, "warmup": warmup,
+           "ms_per_step": ms, "value": pairs / (ms * 1e-3), "unit": UNIT, "iters_per_s": 1e3 / ms,
+           "final_loss": float(loss.item()), "search_kernel_ms": k_ms,
+           "search_frac_of_fp32_peak": FLOP_PER_PAIR * local_pairs / (k_ms * 1e-3) / 1e12 / peak_tf,
+           "our_kernels_per_step": n_ours,
+           "kernels_per_step": {n[:70]: c for n, c in sorted(names.items(), key=lambda kv: -kv[1])}}
+    engine.release()
+    del engine
+    torch.cuda.empty_cache()
+    return ent
+
+
+def candidate_fits(ctx, dev, n_iter=10):
+    """cfg5: one `cano_idx` candidate per rank (README.md:60 of the reference), NO communication during the fits, one
+    NCCL exchange of the energies at the end (engine.fit_candidates -> all_reduce MIN)."""
+    import torch
+    from reart_b200.engine import fit_candidates
+    from reart_b200.synth import make_sequence
+    T, N, P = WORKLOADS["cfg5"]
+    seq = make_sequence(T=T, N=N, P=P, seed=2)
+    sequence = torch.cat((torch.from_numpy(seq["cano"])[None], torch.from_numpy(seq["frames"])), dim=0).to(dev)
+    cands = [int(round(k * T / max(ctx.world_size, 1))) for k in range(ctx.world_size)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.barrier(); torch.cuda.synchronize()
+    e0.record()
+    best, table = fit_candidates(sequence, cands, P, n_iter, ctx=ctx, criterion="loss", use_graph=True)
+    e1.record(); torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    ctx.all_reduce_max_(ms)
+    total_pairs = 2.0 * T * N * N * n_iter * len(cands)
+    return {"workload": "cfg5", "what": f"{len(cands)} cano_idx candidate fits, one per rank, {n_iter} iterations each (graph capture and "
+            "warm-up included in the time), energies exchanged once over NCCL; criterion = final recon loss (the reference's "
+            "total_err needs an N x N assignment per frame, infeasible at 32k points for the reference too)",
+            "candidates": cands, "best_cano_idx": best, "energies": table, "ms_total": float(ms.item()),
+            "value": total_pairs / (float(ms.item()) * 1e-3), "unit": UNIT}
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     args = parse_args()
@@ -224,12 +471,9 @@ def main():
         run_reference_arm(args)
         return
 
-    import numpy as np
     import torch
-    from reart_b200 import _lib, ops
+    from reart_b200 import ops
     from reart_b200.dist import DistContext
-    from reart_b200.engine import RelaxationEngine, tau_schedule
-    from reart_b200.synth import make_sequence
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: reart_b200 has no CPU fallback")
@@ -238,151 +482,158 @@ def main():
     assert world == args.gpus or world == 1, f"launched with WORLD_SIZE={world} but --gpus {args.gpus}"
     dev = torch.device("cuda", ctx.local_rank)
     torch.cuda.set_device(dev)
-    L = _lib.lib()
 
-    T, N, P = WORKLOADS[args.workload]
-    T_total = T if args.scaling == "strong" else T * world
-    seq = make_sequence(T=T_total, N=N, P=P, seed=2)
-    cano_h = torch.from_numpy(seq["cano"]).pin_memory()
-    frames_h = torch.from_numpy(seq["frames"]).pin_memory()
-    if args.workload == "cfg4":
-        from reart_b200.engine import KinematicEngine
-        from reart_b200.synth import kinematic_init
-        kw = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in kinematic_init(seq).items()}
-        engine = KinematicEngine(kw, torch.from_numpy(seq["part"]), cano_h.to(dev), frames_h.to(dev), ctx=ctx,
-                                 use_graph=not args.no_graph)
-    else:
-        engine = RelaxationEngine(cano_h.to(dev), frames_h.to(dev), num_parts=P, ctx=ctx, use_graph=not args.no_graph)
+    engine, cano_h, frames_h, T_total, N, P, _ = make_engine(args.workload, ctx, dev, not args.no_graph, args.scaling,
+                                                             extra_losses=False)
+    T = WORKLOADS[args.workload][0]
     lo, hi = engine.frame_range
     frames_local_h = frames_h[lo:hi]
-    n_iter = 15000                                            # run_robot.py default; only shapes the tau schedule
     pairs_per_step = 2.0 * T_total * N * N
+    uuid = str(torch.cuda.get_device_properties(dev).uuid)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    sampler = ClockSampler(ctx.local_rank, str(torch.cuda.get_device_properties(dev).uuid)) if ctx.is_main else None
+    sampler = ClockSampler(ctx.local_rank, uuid) if ctx.is_main else None
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
-    for i in range(W):
-        engine.step(tau_schedule(i, n_iter, 5.0, 1.0))
-    torch.cuda.synchronize()
-
-    # ---- timed region: K steps, each bracketed by its own events, L2 flushed in between (untimed)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    ctx.barrier(); torch.cuda.synchronize()
-    if sampler:
-        sampler.begin()
-    t_wall0 = time.perf_counter()
-    for i in range(K):
-        flush.fill_(i & 0xff)
-        engine.tau.fill_(tau_schedule(W + i, n_iter, 5.0, 1.0))
-        ev[i][0].record()
-        loss = engine.step()
-        ev[i][1].record()
-    torch.cuda.synchronize(); ctx.barrier()
-    wall_s = time.perf_counter() - t_wall0
-    if sampler:
-        sampler.end()
+    ms_per_step, wall_s, loss = time_engine_steps(engine, ctx, K, W, flush, sampler=sampler)
     clocks = sampler.stop() if sampler else None
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
-    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    ctx.all_reduce_max_(tmax)
-    total_ms = float(tmax.item())
-    ms_per_step = total_ms / K
     value = pairs_per_step / (ms_per_step * 1e-3)
     final_loss = float(loss.item())
 
-    # ---- e2e: host buffers in, loss out, every step (H2D of the step's clouds from pinned memory + D2H of the loss)
+    # ---- e2e: host buffers in, loss out, every step.  The H2D of step i+1 (pinned host clouds -> staging buffer, copy
+    # stream) runs while step i computes; each step then takes its clouds from the staging buffer (D2D), re-packs the
+    # observed frames, runs the iteration and reads the loss back (a host sync per step, like the reference loop's print).
     cano_d, frames_d = engine.cano, engine.frames
     h2d = cano_h.numel() * 4 + frames_local_h.numel() * 4
-    e2e_ms = 0.0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    copy_stream = torch.cuda.Stream()
+    stage_c = [torch.empty_like(cano_d) for _ in range(2)]
+    stage_f = [torch.empty_like(frames_d) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            stage_c[slot].copy_(cano_h, non_blocking=True)
+            stage_f[slot].copy_(frames_local_h, non_blocking=True)
+            ready[slot].record(copy_stream)
+
     K2 = max(3, min(K, 10))
+    for s_ in range(2):
+        consumed[s_].record()
+    torch.cuda.synchronize(); ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    host_loss = None
     for i in range(K2 + 1):
-        flush.fill_(i & 0xff)
-        torch.cuda.synchronize(); ctx.barrier()
-        e0.record()
-        cano_d.copy_(cano_h, non_blocking=True)
-        frames_d.copy_(frames_local_h, non_blocking=True)
+        if i == 1:                                                # step 0 warms the path up; time steps 1..K2
+            flush.fill_(1); torch.cuda.synchronize(); ctx.barrier()
+            e0.record()
+            prefetch(i & 1)                                       # the first timed step's H2D is inside the timed region
+        elif i == 0:
+            prefetch(0)
+        if i + 1 <= K2:
+            prefetch((i + 1) & 1)                                 # next step's clouds: overlaps this step's compute
+        torch.cuda.current_stream().wait_event(ready[i & 1])
+        cano_d.copy_(stage_c[i & 1], non_blocking=True)
+        frames_d.copy_(stage_f[i & 1], non_blocking=True)
+        consumed[i & 1].record()
         engine.frames_packed.copy_(ops.pack_cloud(frames_d))          # observed frames arrive fresh: re-pack
         lval = engine.step()
         host_loss = lval.to("cpu", non_blocking=False)                 # D2H read of the step's result
-        e1.record(); torch.cuda.synchronize()
-        if i > 0:
-            e2e_ms += e0.elapsed_time(e1)
-    t2 = torch.tensor([e2e_ms / K2], dtype=torch.float64, device=dev)
+    e1.record(); torch.cuda.synchronize()
+    t2 = torch.tensor([e0.elapsed_time(e1) / K2], dtype=torch.float64, device=dev)
     ctx.all_reduce_max_(t2)
     e2e_value = pairs_per_step / (float(t2.item()) * 1e-3)
     _ = float(host_loss)
 
     # ---- roofline of the dominant kernel (chamfer_sym_kernel), timed alone with CUDA events on this stream
     Tl = hi - lo
-    keys_a = torch.empty(Tl * N, dtype=torch.int64, device=dev); keys_b = torch.empty(Tl * N, dtype=torch.int64, device=dev)
-    skinned = engine.skinned.detach().contiguous()
-    def search():
-        _lib.check(L.reart_chamfer_sym_search(_lib.ptr(skinned), _lib.ptr(engine.frames_packed), Tl, N, N,
-                                              _lib.ptr(keys_a), _lib.ptr(keys_b), None, 0, _lib.stream_ptr()), "search")
-    for _ in range(2):
-        search()
-    reps = 5
-    k_ms = 0.0
-    for i in range(reps):
-        flush.fill_(i)
-        e0.record(); search(); e1.record(); torch.cuda.synchronize()
-        k_ms += e0.elapsed_time(e1)
-    k_ms /= reps
-    local_pairs = 2.0 * Tl * N * N
+    k_ms, local_pairs, alg_bytes = search_kernel_timing(engine, flush)
     achieved_tf = FLOP_PER_PAIR * local_pairs / (k_ms * 1e-3) / 1e12
-    props = torch.cuda.get_device_properties(dev)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
-    peak_tf = props.multi_processor_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    peak_tf, sm_max_mhz, n_sms, peaks = fp32_peak_tf(dev)
     ms_ffma, ops_ffma = ops.fp32_probe(0, iters=2000, device=dev)
     ffma_tf = 2.0 * ops_ffma / (ms_ffma * 1e-3) / 1e12
-    alg_bytes = Tl * (12.0 * (N + N) + 8.0 * (N + N))                 # read both clouds once, write both key arrays
     roofline = {"bound": "fp32_fma", "kernel": "chamfer_sym_kernel<8,1>", "achieved": achieved_tf, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                "peak_source": f"SMs({props.multi_processor_count}) x 128 lanes x 2 x sm_max_mhz({sm_max_mhz:.0f}) from "
+                "peak_source": f"SMs({n_sms}) x 128 lanes x 2 x sm_max_mhz({sm_max_mhz:.0f}) from "
                                "MEASURED_PEAKS.json (it carries no FP32 entry; BASELINE.md section 3)",
                 "peak_measured_ffma": ffma_tf, "frac_of_measured_ffma": achieved_tf / ffma_tf,
                 "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
                 "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": local_pairs,
+                "executed_flop_note": "one evaluation per unordered pair feeds both directions: executed FLOP = half the credited",
                 "hbm_achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks.get("hbm_gbs"),
                 "traffic": None}
-    try:        # dram bytes of the same kernel from the committed ncu capture (only valid for the captured shape)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_sym_traffic.json")))
-        if tr.get("workload") == args.workload and tr.get("frames_per_launch") == Tl:
-            roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-            roofline["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
-            roofline["algorithmic_bytes_per_launch"] = alg_bytes
-    except Exception:
-        pass
+    for cand in ("r02_sym_traffic.json", "r01_sym_traffic.json"):
+        try:    # dram bytes of the same kernel from a committed `ncu --set full` capture; only for the captured shape
+            tr = json.load(open(os.path.join(ROOT, "profiles", cand)))
+            if tr.get("workload") == args.workload and tr.get("frames_per_launch") == Tl:
+                roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+                roofline["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
+                roofline["traffic_source"] = f"profiles/{cand} (one ncu --set full capture of this kernel at this shape; not re-measured in this run)"
+                roofline["algorithmic_bytes_per_launch"] = alg_bytes
+                break
+        except Exception:
+            pass
 
-    line = None
+    # ---- what one step launches (torch profiler / CUPTI on one eager iteration)
+    n_ours, step_kernels = kernels_of_one_step(engine)
+    table = 8                                                     # head, skin_fwd_sorted, search, energy cols + rows, skin bwd + reduce, tail
+    launches_per_step = n_ours if n_ours else table
+
+    # ---- sustained run
+    sustained = None
+    if args.sustained_s > 0:
+        sustained = sustained_run(engine, ctx, args.sustained_s, ms_per_step, ctx.local_rank, uuid, pairs_per_step,
+                                  k_ms / ms_per_step, peak_tf, sm_max_mhz)
+
+    # ---- sweep over the other BASELINE configs (N=1) / candidate fits (N>1)
+    sweep = None
+    engine.release()
+    del engine
+    torch.cuda.empty_cache()
+    if not args.no_sweep and args.workload == "cfg3_16k":
+        sweep = []
+        if world == 1:
+            for wl in SWEEP:
+                big = WORKLOADS[wl][1] >= 262144
+                try:
+                    sweep.append(sweep_entry(wl, ctx, dev, flush, 2 if big else 5, 3, peak_tf))
+                except Exception as exc:                          # never lose the headline line to a sweep failure
+                    sweep.append({"workload": wl, "error": f"{type(exc).__name__}: {exc}"})
+        else:
+            try:
+                sweep.append(candidate_fits(ctx, dev))
+            except Exception as exc:
+                sweep.append({"workload": "cfg5", "error": f"{type(exc).__name__}: {exc}"})
+
     if ctx.is_main:
-        cpu = None
+        cpu = cpu_py = None
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_reference_throughput(T, N, budget_s=12.0)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            try:
+                cpu_py = reference_python_cpu_baseline(T, N, P)
+            except Exception as exc:
+                cpu_py = {"error": f"{type(exc).__name__}: {exc}"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config_dict(args, T_total, N, P, world),
                 "iters_per_s": 1e3 / ms_per_step, "wall_s_timed_region": wall_s, "final_loss": final_loss,
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-                        "what": "pinned host cano+frames -> H2D -> pack -> full iteration -> loss D2H, per step"},
-                # our kernels per step and rank: segmlp fwd, gumbel fwd, rot6d fwd, skin fwd, chamfer_sym, energy rows +
-                # columns, skin bwd (w + pose), rot6d bwd, gumbel bwd, segmlp bwd
-                # (kinematic model: fk fwd, skin fwd, chamfer_sym, energy rows + columns, skin bwd (w + pose), fk bwd)
-                "gpu_launches": (8 if args.workload == "cfg4" else 12) * K, "cuda_graph": not args.no_graph,
-                "roofline": roofline, "cpu_baseline": cpu}
+                        "what": "per step: pinned host cano+frames -> H2D (copy stream, overlapping the previous step) -> "
+                                "D2D into the engine -> pack -> full iteration -> loss D2H + host sync"},
+                "gpu_launches": launches_per_step * K,
+                "gpu_launches_per_step": launches_per_step,
+                "gpu_launches_source": "torch profiler (CUPTI) on one eager iteration: kernels in namespace reart" if n_ours
+                                       else "table (profiler unavailable)",
+                "step_kernels": {n[:70]: c for n, c in sorted(step_kernels.items(), key=lambda kv: -kv[1])},
+                "cuda_graph": not args.no_graph,
+                "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_reference_python": cpu_py,
+                "sustained": sustained, "sweep": sweep}
         print(json.dumps(line), flush=True)
-    # teardown: captured graphs reference the NCCL communicator, release them first; with more than one rank
-    # leave through os._exit after a final barrier so a slow communicator teardown can never hold the job
-    engine.release()
+    # teardown: captured graphs reference the NCCL communicator; with more than one rank leave through os._exit after
+    # a final barrier so a slow communicator teardown can never hold the job
     ctx.barrier()
     if world > 1:
         sys.stdout.flush(); sys.stderr.flush()

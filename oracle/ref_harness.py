@@ -105,6 +105,10 @@ def install_stubs() -> None:
         k = types.ModuleType("knn_cuda")
         k.KNN = _KNN
         sys.modules["knn_cuda"] = k
+    if "pointnet2_cuda" not in sys.modules:
+        # on a CUDA box the reference imports its compiled PointNet++ extension unconditionally
+        # (networks/pointnet2_utils.py:7-12); the CPU timings made through this harness never call it
+        sys.modules["pointnet2_cuda"] = MagicMock()
     for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors", "matplotlib.cm", "plotly",
                  "plotly.graph_objects", "plotly.express", "imageio", "apted", "apted.helpers", "trimesh", "kaleido"):
         if name not in sys.modules:

@@ -53,8 +53,38 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymPa
     unsigned* colmin = reinterpret_cast<unsigned*>(smem_raw + kSymStages * C::kTileBytes);
     __shared__ __align__(8) uint64_t full_bar[kSymStages];
 
+    int item = blockIdx.x;
+    const int qb = item % p.qblocks;
+    item /= p.qblocks;
+    const int split = item % p.splits;
+    const int b = item / p.splits;
+
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int QB = R * kSymThreads;
+    const int qbase = qb * QB;
+    const float* __restrict__ q = p.a + (int64_t)b * p.na * 3;
+
+    // register r = s*RS + rr holds A point  qbase + warp*32R + s*(32 RS) + lane*RS + rr
+    u64 QX[R], QY[R], QZ[R];
+    float best[R], prev[R];
+    unsigned bch[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = qbase + warp * (32 * R) + (r / RS) * (32 * RS) + lane * RS + (r % RS);
+        float x = INFINITY, y = INFINITY, z = INFINITY;          // out-of-range rows never win a column
+        if (i < p.na) { x = q[3 * i]; y = q[3 * i + 1]; z = q[3 * i + 2]; }
+        QX[r] = pack2(x, x); QY[r] = pack2(y, y); QZ[r] = pack2(z, z);
+        best[r] = INFINITY; prev[r] = INFINITY; bch[r] = 0u;
+    }
+
+    const int chunks_total = p.nb_pad / kChunk;
+    const int cps = (chunks_total + p.splits - 1) / p.splits;
+    const int chunk0 = split * cps;
+    const int nchunks = min(cps, chunks_total - chunk0);
+    const int ntiles = (nchunks + C::kTileChunks - 1) / C::kTileChunks;
+    const float* __restrict__ tp = p.b_packed + (int64_t)b * p.nb_pad * 3 + (int64_t)chunk0 * kChunk * 3;
+    u64* __restrict__ keys_col = p.keys_b + (int64_t)b * p.nb;
+    const unsigned colchunk_base = (unsigned)(qbase / C::kColChunkPts);
 
     if (tid == 0) {
 #pragma unroll
@@ -63,165 +93,149 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymPa
     }
     __syncthreads();
 
-    // Balanced static schedule: the work is B * qblocks row blocks ("pairs") x chunks_total 32-target chunks, linearised
-    // pair-major; CTA c of G owns the contiguous unit range [c U / G, (c+1) U / G) and walks it as at most a few
-    // (pair, chunk range) sub-items.  Every CTA gets the same number of chunks (+-1) whatever the frame count, so a
-    // small shard (strong scaling) no longer pays wave quantisation or 8 prologues per CTA (0.925 of
-    // the ideal at 8 frames with one CTA per (frame, block, split) item).
-    const int chunks_total = p.nb_pad / kChunk;
-    const long long units = (long long)p.B * p.qblocks * chunks_total;
-    long long u = units * blockIdx.x / gridDim.x;
-    const long long u_end = units * (blockIdx.x + 1) / gridDim.x;
-    unsigned kring = 0;                                      // tiles issued so far by this CTA (ring position + parity)
     unsigned cmax = 0u;                                      // largest finite column minimum this thread merged
 
-    while (u < u_end) {
-        const int pair = (int)(u / chunks_total);
-        const int chunk0 = (int)(u - (long long)pair * chunks_total);
-        const int nchunks = (int)min((long long)(chunks_total - chunk0), u_end - u);
-        u += nchunks;
-        const int b = pair / p.qblocks, qb = pair - b * p.qblocks;
-        const int qbase = qb * QB;
-        const float* __restrict__ q = p.a + (int64_t)b * p.na * 3;
+    auto issue = [&](int k) {
+        const int st = k % kSymStages;
+        const int nch = min(C::kTileChunks, nchunks - k * C::kTileChunks);
+        const uint32_t bytes = (uint32_t)nch * kChunk * 12;
+        mbar_expect_tx(&full_bar[st], bytes);
+        tma_bulk_g2s(smem_raw + st * C::kTileBytes, tp + (int64_t)k * C::kTilePoints * 3, bytes, &full_bar[st]);
+    };
+    if (tid == 0) {
+        for (int k = 0; k < min(kSymStages, ntiles); ++k) issue(k);
+    }
 
-        // register r = s*RS + rr holds A point  qbase + warp*32R + s*(32 RS) + lane*RS + rr
-        u64 QX[R], QY[R], QZ[R];
-        float best[R], prev[R];
-        unsigned bch[R];
+    for (int k = 0; k < ntiles; ++k) {
+        const int st = k % kSymStages;
+        mbar_wait(&full_bar[st], (uint32_t)((k / kSymStages) & 1));
+        const int nch = min(C::kTileChunks, nchunks - k * C::kTileChunks);
+        const float4* __restrict__ tile = reinterpret_cast<const float4*>(smem_raw + st * C::kTileBytes);
+        unsigned* __restrict__ cbuf = colmin + (k & 1) * C::kColBufWords;
+        unsigned* __restrict__ cm_w = cbuf + warp * (S * C::kTilePoints);
+        for (int c = 0; c < nch; ++c) {
+            const float4* __restrict__ cg = tile + c * (kChunk / 4 * 3);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int i = qbase + warp * (32 * R) + (r / RS) * (32 * RS) + lane * RS + (r % RS);
-            float x = INFINITY, y = INFINITY, z = INFINITY;          // out-of-range rows never win a column
-            if (i < p.na) { x = q[3 * i]; y = q[3 * i + 1]; z = q[3 * i + 2]; }
-            QX[r] = pack2(x, x); QY[r] = pack2(y, y); QZ[r] = pack2(z, z);
-            best[r] = INFINITY; prev[r] = INFINITY; bch[r] = 0u;
-        }
-
-        const int ntiles = (nchunks + C::kTileChunks - 1) / C::kTileChunks;
-        const float* __restrict__ tp = p.b_packed + (int64_t)b * p.nb_pad * 3 + (int64_t)chunk0 * kChunk * 3;
-        u64* __restrict__ keys_col = p.keys_b + (int64_t)b * p.nb;
-        const unsigned colchunk_base = (unsigned)(qbase / C::kColChunkPts);
-
-        auto issue = [&](int k) {
-            const int st = (int)((kring + (unsigned)k) % kSymStages);
-            const int nch = min(C::kTileChunks, nchunks - k * C::kTileChunks);
-            const uint32_t bytes = (uint32_t)nch * kChunk * 12;
-            mbar_expect_tx(&full_bar[st], bytes);
-            tma_bulk_g2s(smem_raw + st * C::kTileBytes, tp + (int64_t)k * C::kTilePoints * 3, bytes, &full_bar[st]);
-        };
-        if (tid == 0) {
-            for (int k = 0; k < min(kSymStages, ntiles); ++k) issue(k);
-        }
-
-        for (int k = 0; k < ntiles; ++k) {
-            const unsigned kk = kring + (unsigned)k;
-            const int st = (int)(kk % kSymStages);
-            mbar_wait(&full_bar[st], (uint32_t)((kk / kSymStages) & 1u));
-            const int nch = min(C::kTileChunks, nchunks - k * C::kTileChunks);
-            const float4* __restrict__ tile = reinterpret_cast<const float4*>(smem_raw + st * C::kTileBytes);
-            unsigned* __restrict__ cbuf = colmin + (kk & 1u) * C::kColBufWords;
-            unsigned* __restrict__ cm_w = cbuf + warp * (S * C::kTilePoints);
-            for (int c = 0; c < nch; ++c) {
-                const float4* __restrict__ cg = tile + c * (kChunk / 4 * 3);
+            for (int g = 0; g < kChunk / 4; ++g) {
+                const float4 X = cg[3 * g], Y = cg[3 * g + 1], Z = cg[3 * g + 2];
+                const u64 X01 = pack2(X.x, X.y), X23 = pack2(X.z, X.w);
+                const u64 Y01 = pack2(Y.x, Y.y), Y23 = pack2(Y.z, Y.w);
+                const u64 Z01 = pack2(Z.x, Z.y), Z23 = pack2(Z.z, Z.w);
 #pragma unroll
-                for (int g = 0; g < kChunk / 4; ++g) {
-                    const float4 X = cg[3 * g], Y = cg[3 * g + 1], Z = cg[3 * g + 2];
-                    const u64 X01 = pack2(X.x, X.y), X23 = pack2(X.z, X.w);
-                    const u64 Y01 = pack2(Y.x, Y.y), Y23 = pack2(Y.z, Y.w);
-                    const u64 Z01 = pack2(Z.x, Z.y), Z23 = pack2(Z.z, Z.w);
+                for (int s = 0; s < S; ++s) {
+                    float c0, c1, c2, c3;
 #pragma unroll
-                    for (int s = 0; s < S; ++s) {
-                        float c0, c1, c2, c3;
-#pragma unroll
-                        for (int rr = 0; rr < RS; ++rr) {
-                            const int r = s * RS + rr;
-                            float a0, a1, a2, a3;
-                            unpack2(sqdist_pair(QX[r], QY[r], QZ[r], X01, Y01, Z01), a0, a1);
-                            unpack2(sqdist_pair(QX[r], QY[r], QZ[r], X23, Y23, Z23), a2, a3);
-                            best[r] = min3(best[r], a0, a1);
-                            best[r] = min3(best[r], a2, a3);
-                            if (rr == 0) { c0 = a0; c1 = a1; c2 = a2; c3 = a3; }
-                            else { c0 = fminf(c0, a0); c1 = fminf(c1, a1); c2 = fminf(c2, a2); c3 = fminf(c3, a3); }
-                        }
-                        const unsigned m0 = __reduce_min_sync(0xffffffffu, __float_as_uint(c0));
-                        const unsigned m1 = __reduce_min_sync(0xffffffffu, __float_as_uint(c1));
-                        const unsigned m2 = __reduce_min_sync(0xffffffffu, __float_as_uint(c2));
-                        const unsigned m3 = __reduce_min_sync(0xffffffffu, __float_as_uint(c3));
-                        if (lane == 0)
-                            *reinterpret_cast<uint4*>(cm_w + s * C::kTilePoints + c * kChunk + 4 * g) = make_uint4(m0, m1, m2, m3);
+                    for (int rr = 0; rr < RS; ++rr) {
+                        const int r = s * RS + rr;
+                        float a0, a1, a2, a3;
+                        unpack2(sqdist_pair(QX[r], QY[r], QZ[r], X01, Y01, Z01), a0, a1);
+                        unpack2(sqdist_pair(QX[r], QY[r], QZ[r], X23, Y23, Z23), a2, a3);
+                        best[r] = min3(best[r], a0, a1);
+                        best[r] = min3(best[r], a2, a3);
+                        if (rr == 0) { c0 = a0; c1 = a1; c2 = a2; c3 = a3; }
+                        else { c0 = fminf(c0, a0); c1 = fminf(c1, a1); c2 = fminf(c2, a2); c3 = fminf(c3, a3); }
                     }
-                }
-                const unsigned gid = (unsigned)(chunk0 + k * C::kTileChunks + c);
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if (best[r] < prev[r]) bch[r] = gid;
-                    prev[r] = best[r];
-                }
-            }
-            __syncthreads();                                   // tile consumed, per-warp column minima complete
-            if (tid == 0 && k + kSymStages < ntiles) issue(k + kSymStages);
-            // fold the warps x S column arrays of this tile and merge into the global column keys; (warp, s) in
-            // increasing order is increasing A index, so a strict < keeps the lowest chunk on ties
-            const int npts = nch * kChunk;
-            const int jbase = (chunk0 + k * C::kTileChunks) * kChunk;
-            for (int e = tid; e < npts; e += kSymThreads) {
-                const int j = jbase + e;
-                if (j < p.nb) {
-                    unsigned m = cbuf[e];
-                    unsigned wbest = 0;
-#pragma unroll
-                    for (int ws = 1; ws < kSymWarps * S; ++ws) {
-                        const unsigned v = cbuf[ws * C::kTilePoints + e];
-                        if (v < m) { m = v; wbest = (unsigned)ws; }
-                    }
-                    const u64 key = ((u64)m << 32) | (u64)(colchunk_base + wbest);
-                    if (p.qblocks == 1) keys_col[j] = key;
-                    else atomicMin(&keys_col[j], key);
-                    if (m < 0x7f800000u) cmax = max(cmax, m);
+                    const unsigned m0 = __reduce_min_sync(0xffffffffu, __float_as_uint(c0));
+                    const unsigned m1 = __reduce_min_sync(0xffffffffu, __float_as_uint(c1));
+                    const unsigned m2 = __reduce_min_sync(0xffffffffu, __float_as_uint(c2));
+                    const unsigned m3 = __reduce_min_sync(0xffffffffu, __float_as_uint(c3));
+                    if (lane == 0)
+                        *reinterpret_cast<uint4*>(cm_w + s * C::kTilePoints + c * kChunk + 4 * g) = make_uint4(m0, m1, m2, m3);
                 }
             }
-            // cbuf (kk & 1) is rewritten two tiles later, after the __syncthreads of the next tile which every thread
-            // reaches only after finishing this fold
-        }
-        kring += (unsigned)ntiles;
-
-        u64* __restrict__ keys_row = p.keys_a + (int64_t)b * p.na;
+            const unsigned gid = (unsigned)(chunk0 + k * C::kTileChunks + c);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int i = qbase + warp * (32 * R) + (r / RS) * (32 * RS) + lane * RS + (r % RS);
-            if (i < p.na) {
-                const u64 key = ((u64)__float_as_uint(best[r]) << 32) | (u64)bch[r];
-                atomicMin(&keys_row[i], key);
+            for (int r = 0; r < R; ++r) {
+                if (best[r] < prev[r]) bch[r] = gid;
+                prev[r] = best[r];
             }
         }
-        __syncthreads();                                       // the last fold's reads of cbuf precede the next sub-item's writes
+        __syncthreads();                                   // tile consumed, per-warp column minima complete
+        if (tid == 0 && k + kSymStages < ntiles) issue(k + kSymStages);
+        // fold the warps x S column arrays of this tile and merge into the global column keys; (warp, s) in
+        // increasing order is increasing A index, so a strict < keeps the lowest chunk on ties
+        const int npts = nch * kChunk;
+        const int jbase = (chunk0 + k * C::kTileChunks) * kChunk;
+        for (int e = tid; e < npts; e += kSymThreads) {
+            const int j = jbase + e;
+            if (j < p.nb) {
+                unsigned m = cbuf[e];
+                unsigned wbest = 0;
+#pragma unroll
+                for (int ws = 1; ws < kSymWarps * S; ++ws) {
+                    const unsigned v = cbuf[ws * C::kTilePoints + e];
+                    if (v < m) { m = v; wbest = (unsigned)ws; }
+                }
+                const u64 key = ((u64)m << 32) | (u64)(colchunk_base + wbest);
+                if (p.qblocks == 1) keys_col[j] = key;
+                else atomicMin(&keys_col[j], key);
+                if (m < 0x7f800000u) cmax = max(cmax, m);
+            }
+        }
+        // cbuf (k & 1) is rewritten in tile k+2, after the __syncthreads of tile k+1 which every thread reaches
+        // only after finishing this fold
     }
 
     if (p.col_bound) {                                       // one atomic per warp: bound for the fixed-point energy scatter
         cmax = __reduce_max_sync(0xffffffffu, cmax);
         if (lane == 0 && cmax) atomicMax(p.col_bound, cmax);
     }
+
+    u64* __restrict__ keys_row = p.keys_a + (int64_t)b * p.na;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = qbase + warp * (32 * R) + (r / RS) * (32 * RS) + lane * RS + (r % RS);
+        if (i < p.na) {
+            const u64 key = ((u64)__float_as_uint(best[r]) << 32) | (u64)bch[r];
+            if (p.splits == 1) keys_row[i] = key;
+            else atomicMin(&keys_row[i], key);
+        }
+    }
+}
+
+// (Measured and rejected in round 2: a persistent one-wave schedule that gives each of 2 x 148 CTAs an equal contiguous
+// share of the (row block, chunk) units -- 3.98 ms instead of 3.69 ms at 64 frames, 0.520 instead of 0.499 ms at 8: with
+// equal static shares the slowest CTA sets the time, while one CTA per item lets the hardware scheduler absorb the
+// SM-to-SM variance.  profiles/r02_scaling.md.)
+// Number of target splits per (frame, query block).  CTAs map 1:1 to work items and two are resident per SM, so
+// the grid runs in waves of 2*148 CTAs: pick the split count whose item total wastes the least of its last wave
+// (strong scaling leaves few frames per GPU, where a bad count costs 15-25 % of the kernel), preferring fewer,
+// larger items on ties, and keeping at least one full tile (512 targets) per item.
+static int sym_choose_splits(int64_t B, int qblocks, int chunks_total, int tile_chunks) {
+    const int64_t slots = 2 * 148;
+    const int64_t base = std::max<int64_t>(1, B * qblocks);
+    // normally at least one full tile (512 targets) per item; when even that leaves SMs idle go down to 128 targets
+    int max_s = std::max(1, chunks_total / std::max(tile_chunks, 16));
+    if (base * max_s < slots) max_s = std::max(max_s, chunks_total / 4);
+    if (base >= 8 * slots) return 1;                        // plenty of items already: tail < 1/8 wave
+    int best_s = 1;
+    double best_eff = -1.0;
+    for (int sp = 1; sp <= max_s; ++sp) {
+        const int64_t items = base * sp;
+        const int64_t waves = ceil_div(items, slots);
+        double eff = (double)items / (double)(waves * slots);
+        if (waves >= 8) eff = std::max(eff, 0.97);         // many waves: the tail no longer matters
+        // each item pays a fixed prologue/epilogue (~2 % of a 1024-target item): charge it
+        const double per_item_targets = (double)chunks_total * kChunk / sp;
+        eff *= per_item_targets / (per_item_targets + 24.0);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_s = sp; }
+    }
+    return best_s;
 }
 
 template <int R, int S>
 static int launch_sym_rs(SymParams& p, cudaStream_t stream) {
     using C = SymCfg<R, S>;
     p.qblocks = (int)ceil_div(p.na, R * kSymThreads);
-    p.splits = 1;                                              // (kept for the struct's users; the schedule is per CTA now)
+    p.splits = sym_choose_splits(p.B, p.qblocks, p.nb_pad / kChunk, C::kTileChunks);
+    if (p.variant >= 16) p.splits = std::max(1, std::min(p.variant / 16, p.nb_pad / kChunk));   // tuning override
     p.col_chunk_pts = C::kColChunkPts;
-    const int64_t units = (int64_t)p.B * p.qblocks * (p.nb_pad / kChunk);
-    if (units <= 0) return kOk;
-    // one wave of 2 CTAs per SM, every CTA an equal share of the (row block, 32-target chunk) units; tiny problems get
-    // fewer CTAs so that a share is at least 4 chunks (128 targets)
-    int dev_sms = 148;
-    {
-        int devid = 0;
-        if (cudaGetDevice(&devid) == cudaSuccess) cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, devid);
-    }
-    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(2 * (int64_t)dev_sms, units / 4));
-    // merge keys start at +max: row blocks are split across CTAs (atomicMin), columns meet when there are several
-    // row blocks per frame; one memset when the two arrays are neighbours in the workspace (every pipeline of capi.cu)
-    const bool need_a = !p.keys_preset, need_b = p.qblocks > 1 && !p.keys_preset;
+    const int64_t items = (int64_t)p.B * p.qblocks * p.splits;
+    if (items <= 0) return kOk;
+    if (items > 0x7fffffff) return kErrUnsupported;
+    // merge keys start at +max wherever partial results meet through atomicMin; one memset when the two arrays are
+    // neighbours in the workspace (they are in every pipeline of capi.cu)
+    const bool need_a = p.splits > 1 && !p.keys_preset, need_b = p.qblocks > 1 && !p.keys_preset;
     const size_t bytes_a = sizeof(u64) * (size_t)p.B * p.na, bytes_b = sizeof(u64) * (size_t)p.B * p.nb;
     const char* a0 = reinterpret_cast<const char*>(p.keys_a);
     const char* b0 = reinterpret_cast<const char*>(p.keys_b);
@@ -240,7 +254,7 @@ static int launch_sym_rs(SymParams& p, cudaStream_t stream) {
             return kErrLaunch;
         if (devid >= 0 && devid < 64) attr_done[devid] = true;
     }
-    chamfer_sym_kernel<R, S><<<(unsigned)grid, kSymThreads, C::kSmem, stream>>>(p);
+    chamfer_sym_kernel<R, S><<<(unsigned)items, kSymThreads, C::kSmem, stream>>>(p);
     REART_CHECK_LAUNCH();
     return kOk;
 }

@@ -242,8 +242,9 @@ def halo_from_previous_rank(x_last: torch.Tensor, ctx: DistContext) -> torch.Ten
 
 
 def select_best_candidate(ctx: DistContext, energy: float, device=None) -> Tuple[int, List[float]]:
-    """cano_idx candidate fits are independent runs, one per rank (README.md:60; energy = total_err,
-    run_robot.py:314): gather the scalars and return (rank of the lowest energy, all energies)."""
+    """cano_idx candidate fits are independent runs, one per rank (README.md:60): gather one scalar energy per rank and
+    return (rank of the lowest energy, all energies).  The reference's energy is total_err (run_robot.py:306-314); that
+    is what ``engine.candidate_energy`` / ``engine.fit_candidates(criterion="total_err")`` compute."""
     energies = ctx.all_gather_scalar(energy, device=device)
     best = min(range(len(energies)), key=lambda i: (energies[i], i))
     return best, energies

@@ -19,15 +19,33 @@ from ..knn_module import KNN
 
 # The reference's ChamferDistance.forward runs TWO searches back to back, knn_points(src, tgt) then
 # knn_points(tgt, src) (utils/chamfer.py:78-94).  Every distance is symmetric, so the first call evaluates each
-# pair once for both directions (chamfer_sym.cu) and parks the reverse result here; the second call, recognised
-# by the swapped (data_ptr, version, shape) signature, is answered from the cache.  The entry holds strong
-# references to both tensors, so their storage cannot be recycled for other data while the entry is alive (also
-# under torch.no_grad(), where autograd keeps nothing); any other call drops it.
-_reverse_cache = {"sig": None, "idx": None, "dists": None, "keep": None}
+# pair once for both directions (chamfer_sym.cu) and parks the reverse result here; the second call is answered from
+# the cache.  The pairing is pinned to ONE invocation of ChamferDistance.forward: the cache entry remembers the Python
+# frame object of the enclosing forward() and is honoured only by a call made from that very frame (plus the swapped
+# (data_ptr, version, shape) signature).  Outside a ChamferDistance.forward nothing is cached, so raw-pointer writers
+# that do not bump tensor versions can never be served a stale result by a later, unrelated call.  The entry holds
+# strong references to both tensors (their storage cannot be recycled while it is alive); any other call drops it.
+_reverse_cache = {"sig": None, "idx": None, "dists": None, "keep": None, "frame": None}
 
 
 def _sig(a, b):
     return (a.data_ptr(), a._version, tuple(a.shape), b.data_ptr(), b._version, tuple(b.shape), a.device.index)
+
+
+def _enclosing_chamfer_forward():
+    """The frame of the ChamferDistance.forward this call is (transitively) made from, or None."""
+    f = sys._getframe(2)
+    for _ in range(16):
+        if f is None:
+            return None
+        if f.f_code.co_name == "forward" and type(f.f_locals.get("self")).__name__ == "ChamferDistance":
+            return f
+        f = f.f_back
+    return None
+
+
+def _drop_cache():
+    _reverse_cache.update(sig=None, idx=None, dists=None, keep=None, frame=None)
 
 
 def _knn_points_idx(p1, p2, lengths1, lengths2, K, version):
@@ -41,15 +59,16 @@ def _knn_points_idx(p1, p2, lengths1, lengths2, K, version):
     p1c, p2c = p1.float().contiguous(), p2.float().contiguous()
     B, P1, _ = p1c.shape
     P2 = p2c.shape[1]
-    if _reverse_cache["sig"] == _sig(p1c, p2c):
+    fwd_frame = _enclosing_chamfer_forward()
+    if fwd_frame is not None and _reverse_cache["frame"] is fwd_frame and _reverse_cache["sig"] == _sig(p1c, p2c):
         idx, dists = _reverse_cache["idx"], _reverse_cache["dists"]
-        _reverse_cache.update(sig=None, idx=None, dists=None, keep=None)
+        _drop_cache()
         return idx, dists
-    _reverse_cache.update(sig=None, idx=None, dists=None, keep=None)
+    _drop_cache()
     dists = torch.empty(B, P1, 1, dtype=torch.float32, device=p1.device)
     idx = torch.empty(B, P1, 1, dtype=torch.int64, device=p1.device)
-    if P1 >= 256 and P2 >= 256:
-        # likely the first half of a bidirectional Chamfer: compute both directions now
+    if fwd_frame is not None and P1 >= 256 and P2 >= 256:
+        # the first search of a ChamferDistance.forward: compute both directions now
         rd = torch.empty(B, P2, 1, dtype=torch.float32, device=p1.device)
         ri = torch.empty(B, P2, 1, dtype=torch.int64, device=p1.device)
         nbytes = L.reart_chamfer_workspace_bytes(B, P1, P2)
@@ -58,7 +77,7 @@ def _knn_points_idx(p1, p2, lengths1, lengths2, K, version):
             _lib.check(L.reart_chamfer_bidir_fwd(_lib.ptr(p1c), _lib.ptr(p2c), B, P1, P2, _lib.ptr(dists), _lib.ptr(idx),
                                                  _lib.ptr(rd), _lib.ptr(ri), _lib.ptr(ws), nbytes, _lib.stream_ptr()),
                        "reart_chamfer_bidir_fwd")
-        _reverse_cache.update(sig=_sig(p2c, p1c), idx=ri, dists=rd, keep=(p1c, p2c))
+        _reverse_cache.update(sig=_sig(p2c, p1c), idx=ri, dists=rd, keep=(p1c, p2c), frame=fwd_frame)
         return idx, dists
     nbytes = L.reart_knn1_workspace_bytes(B, P1, P2)
     ws = _lib.workspace(nbytes, p1.device)

@@ -56,7 +56,11 @@ class _EngineBase:
         self.optimizer.zero_grad(set_to_none=True)
         loss = self._iteration()
         self.sink.extra[0:1].copy_(loss.detach().reshape(1))
-        loss.backward()
+        self.sink.active = True
+        try:
+            loss.backward()
+        finally:
+            self.sink.active = False
         total = self.sink.extra[0]
         self.optimizer.step()
         return total
@@ -132,6 +136,9 @@ class RelaxationEngine(_EngineBase):
         # the flow loss couples consecutive frames: under frame sharding each rank evaluates the pairs whose second
         # frame it owns and receives ONE skinned frame (the previous rank's last) per iteration (dist.py)
         dev = cano.device
+        if frames.shape[0] < self.ctx.world_size:
+            raise ValueError(f"{frames.shape[0]} frames cannot be sharded over {self.ctx.world_size} ranks: every rank must "
+                             "own at least one frame (an empty shard would skip the step's collectives)")
         lo, hi = self.ctx.frames(frames.shape[0])
         self.frame_range = (lo, hi)
         self.total_frames = int(frames.shape[0])
@@ -313,6 +320,8 @@ class KinematicEngine(_EngineBase):
         super().__init__(ctx, use_graph)
         from .knn_module import KNN
         dev = cano.device
+        if frames.shape[0] < self.ctx.world_size:
+            raise ValueError(f"{frames.shape[0]} frames cannot be sharded over {self.ctx.world_size} ranks")
         lo, hi = self.ctx.frames(frames.shape[0])
         self.frame_range = (lo, hi)
         self.cano = cano.float().contiguous()
@@ -363,13 +372,48 @@ def fit_relaxation(cano: torch.Tensor, frames: torch.Tensor, num_parts: int, n_i
     return eng, losses
 
 
+@torch.no_grad()
+def candidate_energy(engine: "RelaxationEngine", cano_idx: int, merge_thr: float = 3e-2, merge_it: int = 2,
+                     cano_dist_thr: float = 1e-2, lambda_joint: float = 100.0) -> float:
+    """The reference's model-selection energy of a finished relaxation fit (run_robot.py:224-240, 306-314):
+    ``total_err = 100 * ass_err + screw_err + group_err`` after the snapshot tail (denoise -> merging_wrapper ->
+    mst_wrapper -> extract_kinematic) has turned the soft segmentation into a kinematic tree."""
+    from .chamfer import ChamferDistance
+    from .knn_module import KNN
+    from .model_utils import compute_ass_err, compute_group_temporal_err, compute_pc_transform
+    from .structure import (compute_screw_cost, denoise_seg_label, extract_kinematic, merging_wrapper, mst_wrapper)
+    cano, frames = engine.cano, engine.frames
+    _, seg_part, trans_list = engine.model(cano)
+    cd, knn = ChamferDistance(), KNN(k=1, transpose_mode=True)
+    seg_part = denoise_seg_label(seg_part, cano, knn, min_num=20)
+    if len(torch.unique(seg_part)) > 1:
+        seg_part = merging_wrapper(seg_part, trans_list, cano, cd, merge_thr, n_it=merge_it)
+    conn = mst_wrapper(seg_part, trans_list, cano, cd, verbose=False, num_fps=20, cano_dist_thr=cano_dist_thr,
+                       joint_cost_weight=lambda_joint)
+    seg_part, trans_list, conn = extract_kinematic(seg_part, trans_list, conn)
+    pred = compute_pc_transform(cano, trans_list, seg_part)
+    ass_err = 100.0 * compute_ass_err(pred, frames, use_nproc=True)
+    screw_err = compute_screw_cost(trans_list, conn)
+    complete = torch.cat((pred[:cano_idx], cano[None], pred[cano_idx:]), dim=0)
+    group_err = compute_group_temporal_err(complete, seg_part)
+    return float(ass_err + screw_err + group_err)
+
+
 def fit_candidates(sequence: torch.Tensor, candidates, num_parts: int, n_iter: int, ctx: Optional[DistContext] = None,
-                   **kwargs):
+                   criterion: str = "total_err", **kwargs):
     """``cano_idx`` model selection (README.md:60 of the reference: fit every candidate canonical frame, keep the
     lowest energy).  The fits are independent runs: with G ranks, rank r fits candidates r, r+G, ... on its own GPU
-    with NO communication; one gather of the final energies picks the winner.  ``sequence`` [T+1,N,3] is the
+    with NO communication; one exchange of the final energies picks the winner.  ``sequence`` [T+1,N,3] is the
     complete sequence; candidate c uses frame c as the canonical cloud and the others as observations.
+
+    ``criterion="total_err"`` (default) is the reference's selection energy, ``100 * ass_err + screw_err + group_err``
+    (run_robot.py:306-314), evaluated by ``candidate_energy`` after each fit; a fit whose structure stage cannot be
+    built (degenerate collapse, SURVEY Q21: the reference crashes there) gets energy +inf.  ``criterion="loss"`` keeps
+    the final training loss instead -- NOT the reference's criterion (it favours over-segmented fits); it exists for
+    clouds too large for the N x N assignment inside ``ass_err`` (which the reference cannot run either).
     Returns (best_cano_idx, {cano_idx: energy}) on every rank."""
+    if criterion not in ("total_err", "loss"):
+        raise ValueError("criterion must be 'total_err' or 'loss'")
     ctx = ctx or DistContext()
     mine = {}
     for k, c in enumerate(candidates):
@@ -377,8 +421,15 @@ def fit_candidates(sequence: torch.Tensor, candidates, num_parts: int, n_iter: i
             continue
         cano = sequence[c]
         frames = torch.cat((sequence[:c], sequence[c + 1:]), dim=0)
-        _, losses = fit_relaxation(cano, frames, num_parts, n_iter, ctx=DistContext(), **kwargs)   # local, unsharded
-        mine[int(c)] = losses[-1]
+        eng, losses = fit_relaxation(cano, frames, num_parts, n_iter, ctx=DistContext(), **kwargs)   # local, unsharded
+        if criterion == "loss":
+            mine[int(c)] = losses[-1]
+        else:
+            try:
+                mine[int(c)] = candidate_energy(eng, int(c))
+            except (ValueError, AssertionError, RuntimeError, IndexError):
+                mine[int(c)] = float("inf")
+        eng.release()
     # one exchange of len(candidates) scalars: every rank fills in the energies it computed (+inf elsewhere), MIN-reduce
     dev = sequence.device if (sequence.is_cuda and ctx.backend != "gloo") else torch.device("cpu")
     vec = torch.full((len(candidates),), float("inf"), dtype=torch.float64, device=dev)

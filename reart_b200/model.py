@@ -164,9 +164,10 @@ class KinematicModel(nn.Module):
         """k=1 label transfer (networks/model.py:138).  When the query IS the stored canonical cloud the
         answer is constant over the optimisation: it is computed once and cached."""
         if input_pc is self.cano_pc or (input_pc.shape == self.cano_pc.shape and input_pc.data_ptr() == self.cano_pc.data_ptr()):
-            if self._label_cache is None:
-                self._label_cache = knn_query(input_pc, self.cano_pc, self.seg_part, self.knn)
-            return self._label_cache
+            key = (self.cano_pc.data_ptr(), self.cano_pc._version, self.seg_part.data_ptr(), self.seg_part._version)
+            if self._label_cache is None or self._label_cache[0] != key:      # also invalidated by reassigning seg_part
+                self._label_cache = (key, knn_query(input_pc, self.cano_pc, self.seg_part, self.knn))
+            return self._label_cache[1]
         return knn_query(input_pc, self.cano_pc, self.seg_part, self.knn)
 
     def transforms(self, **kwargs):

@@ -104,6 +104,8 @@ class _SegMlp(Function):
         N, H, P = x.shape[0], w0.shape[0], w2.shape[0]
         g = _f32c(g)
         sink = ctx.sink
+        if sink is not None and not sink.active:
+            sink = None                                        # outside a synchronized engine step: plain gradients, no collective
         if sink is None:
             flat = torch.empty(4 * H + P * H, dtype=torch.float32, device=x.device)
             gw0, gb0, gw2 = flat[:3 * H].view(H, 3), flat[3 * H:4 * H], flat[4 * H:].view(P, H)
@@ -130,6 +132,11 @@ class GradSink:
         self.flat = torch.zeros(self.n_grad + extra_scalars, dtype=torch.float32, device=device)
         self.extra = self.flat[self.n_grad:]
         self.reducer = reducer
+        # The bucket is written in place and reduced (a collective!) from inside the backward, and the returned gradients
+        # alias it.  That is only sound inside the engine's synchronized step (all ranks run the same backward, grads are
+        # consumed by the optimiser before the next one); any other backward through the seg logits -- ik() on a BaseModel,
+        # an evaluation on one rank -- gets fresh gradient tensors and no collective.
+        self.active = False
 
     def reduce(self):
         if self.reducer is not None:
