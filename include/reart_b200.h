@@ -244,6 +244,26 @@ REART_API int reart_knn3_blend(const float* query, const float* ref_cat, const f
                                void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Assignment loss (run_robot.py:164-187, run_real.py:180-203, run_sapien.py:179-203; utils/model_utils.py:85-103).
+ * reart_lap: for each of B frames the exactly optimal one-to-one matching of n source samples to n target samples
+ *   under the float32 Euclidean cost (what linear_sum_assignment(torch.cdist(pc_src, pc_tgt)) returns on the host in
+ *   the reference), by shortest augmenting paths with float64 duals, costs formed on the fly -- no n x n matrix, no
+ *   D2H copy, no host solver.  Source sample i of frame b is src[b][src_idx[i]] (src_idx may be null: i itself);
+ *   src has src_points points per frame.  col4row [B,n] int32: target sample matched to source sample i (rows in
+ *   order, like scipy's row_ind = arange).  total [B] float64 (optional): the assignment's cost.  n <= 4096.
+ *   dual_u [B,n] float64 (optional): the row duals of the solve are written there; with warm_start != 0 they are also
+ *   READ as the starting duals (a previous solve of slightly different clouds -- the refresh every assign_gap
+ *   iterations): any starting duals give the same optimal cost, good ones leave almost no augmentation to do.
+ * reart_assign_loss_grad: loss += lambda * sum |skinned[t, src_idx[i]] - tgt[t, col4row[t,i]]|^2 and its gradient
+ *   into g_skinned [T,N,3] (accumulate != 0: added to what is there; else written at the sampled points only).
+ * ------------------------------------------------------------------------------------------- */
+REART_API int reart_lap(const float* src, const int64_t* src_idx, int64_t src_points, const float* tgt, int64_t B,
+                        int64_t n, int32_t* col4row, double* total, double* dual_u, int warm_start, void* stream);
+REART_API int reart_assign_loss_grad(const float* skinned, const int64_t* src_idx, const float* tgt,
+                                     const int32_t* col4row, int64_t T, int64_t N, int64_t n, float lambda,
+                                     float* g_skinned, int accumulate, double* loss, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Furthest point sampling / ball query (the two reachable kernels of the reference's PointNet++ extension).
  * Replace pointnet2_cuda.furthest_point_sampling_wrapper(B, N, npoint, xyz, temp, out) and
  * pointnet2_cuda.ball_query_wrapper(B, N, npoint, radius, nsample, new_xyz, xyz, idx)

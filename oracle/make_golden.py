@@ -478,6 +478,74 @@ def gen_nao_eval(ref):
     print("nao_eval.npz", rows)
 
 
+def gen_assign(ref):
+    """The assignment-loss refresh block of run_robot.py:164-187 run with the reference's own helpers on the nao demo
+    (skinned cloud = the base-2 relaxation result, KAT-A), FPS with the CUDA start index 0:
+    sample indices, per-frame optimal assignment cost, the matching, and the loss."""
+    import importlib
+    from scipy.optimize import linear_sum_assignment
+    pn2 = importlib.import_module("networks.pointnet2_utils")
+    mu = ref.model_utils
+    res = pickle.load(open(f"{REF}/demo_data/pretrained/nao/base-2/result_14999.pkl", "rb"))
+    cano = torch.from_numpy(res["cano_pc"]).float()
+    pc_list = torch.from_numpy(res["pc_list"]).float()
+    pose = torch.from_numpy(res["pred_pose_list"]).float()
+    part = torch.from_numpy(res["pred_cano_part"]).long()
+    pc_trans_list = mu.compute_pc_transform(cano, pose, part)
+    downsample, lambda_assign = 4, 3e-1
+    num_fps = pc_trans_list.shape[1] // downsample
+    src_idx = _fps_from_zero(cano.unsqueeze(dim=0), num_fps).expand(pc_trans_list.shape[0], num_fps)
+    pc_src = pn2.index_points(pc_trans_list, src_idx)
+    tgt_idx = _fps_from_zero(pc_list, num_fps)
+    pc_tgt = pn2.index_points(pc_list, tgt_idx)
+    cost = torch.cdist(pc_src, pc_tgt).cpu().numpy()
+    indices = [linear_sum_assignment(c) for c in cost]
+    assign_indices = [(torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)) for i, j in indices]
+    ass_src_idx = mu.get_src_permutation_idx(assign_indices)
+    ass_tgt_idx = mu.get_tgt_permutation_idx(assign_indices)
+    ass_loss = lambda_assign * ((pc_src[ass_src_idx] - pc_tgt[ass_tgt_idx]) ** 2).sum(dim=-1).sum()
+    totals = np.array([c[i, j].astype(np.float64).sum() for c, (i, j) in zip(cost, indices)])
+    np.savez_compressed(os.path.join(OUT, "assign.npz"), src_idx=src_idx[0].numpy().astype(np.int16),
+                        tgt_idx=tgt_idx.numpy().astype(np.int16), col_ind=np.stack([j for _, j in indices]).astype(np.int16),
+                        totals=totals, ass_loss=np.float64(ass_loss.item()), lambda_assign=np.float64(lambda_assign),
+                        downsample=np.int64(downsample))
+    print("assign.npz", totals.sum(), ass_loss.item())
+
+
+def gen_total_err(ref):
+    """The model-selection energy of run_robot.py:224-240,306-314 for the shipped base-2 relaxation checkpoint on the nao
+    demo, computed by the reference's own functions (structure tail with the CUDA FPS start index, then
+    total_err = 100 * ass_err + screw_err + group_err)."""
+    import importlib
+    g = importlib.import_module("utils.graph_utils")
+    k = importlib.import_module("utils.kinematic_utils")
+    mu = ref.model_utils
+    g.farthest_point_sample = _fps_from_zero
+    cd = ref.chamfer.ChamferDistance()
+    res = pickle.load(open(f"{REF}/demo_data/pretrained/nao/base-2/result_14999.pkl", "rb"))
+    cano = torch.from_numpy(res["cano_pc"]).float()
+    pc_list = torch.from_numpy(res["pc_list"]).float()
+    cidx = int(res["cano_idx"])
+    cb = torch.load(f"{REF}/demo_data/pretrained/nao/base-2/model.pth.tar", map_location="cpu", weights_only=False)
+    bm = ref.model.BaseModel(num_parts=20, pose_len=pc_list.shape[0])
+    bm.load_state_dict(cb["state_dict"], strict=False)
+    with torch.no_grad():
+        _, seg_part, trans_list = bm(cano)
+    seg_part = g.denoise_seg_label(seg_part, cano, ref.KNN(k=1, transpose_mode=True), min_num=20)
+    seg_part = g.merging_wrapper(seg_part, trans_list, cano, cd, 3e-2, n_it=2)
+    conn = g.mst_wrapper(seg_part, trans_list, cano, cd, verbose=False, num_fps=20, cano_dist_thr=1e-2, joint_cost_weight=100)
+    seg_part, trans_list, conn = k.extract_kinematic(seg_part, trans_list, conn)
+    pred = mu.compute_pc_transform(cano, trans_list, seg_part)
+    ass_err = 100 * mu.compute_ass_err(pred, pc_list, use_nproc=True)
+    screw_err = g.compute_screw_cost(trans_list, conn)
+    complete = torch.cat((pred[:cidx], cano[None], pred[cidx:]), dim=0)
+    group_err = mu.compute_group_temporal_err(complete, seg_part)
+    total = ass_err + screw_err + group_err
+    np.savez_compressed(os.path.join(OUT, "total_err.npz"), ass_err=np.float64(float(ass_err)), screw_err=np.float64(float(screw_err)),
+                        group_err=np.float64(float(group_err)), total_err=np.float64(float(total)))
+    print("total_err.npz", float(ass_err), float(screw_err), float(group_err), float(total))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -489,6 +557,8 @@ def main():
     gen_nao(ref)
     gen_structure(ref)
     gen_nao_eval(ref)
+    gen_assign(ref)
+    gen_total_err(ref)
 
 
 if __name__ == "__main__":

@@ -75,6 +75,8 @@ SIGNATURES.update({
     "reart_relax_head": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp, _vp, _vp]),
     "reart_relax_tail_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i64]),
     "reart_relax_tail": (_c_int, [ctypes.POINTER(RelaxTailArgs), _vp]),
+    "reart_lap": (_c_int, [_vp, _vp, _c_i64, _vp, _c_i64, _c_i64, _vp, _vp, _vp, _c_int, _vp]),
+    "reart_assign_loss_grad": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, ctypes.c_float, _vp, _c_int, _vp, _vp]),
 })
 
 _lib = None

@@ -1,21 +1,26 @@
 """Assignment loss of the run scripts (run_robot.py:164-187, run_real.py:180-203, run_sapien.py:179-203).
 
-Every ``assign_gap`` iterations the reference FPS-samples the canonical cloud and every observed frame, builds
-the [T,n,n] Euclidean cost, solves one Hungarian assignment per frame on the CPU inside a freshly spawned
-``multiprocessing.Pool`` (utils/model_utils.py:85-89) and then penalises the squared distance of the
-matched pairs.  Here: FPS for all frames in ONE launch (``reart_fps``), the cost matrix stays a torch op, and
-the Hungarian solves run in a persistent worker pool created once (a GPU LAP is future work).
+Every ``assign_gap`` iterations the reference FPS-samples the canonical cloud and every observed frame, builds the
+[T,n,n] Euclidean cost with ``torch.cdist``, copies it to the host and solves one Hungarian assignment per frame
+(``scipy.optimize.linear_sum_assignment``, optionally inside a ``multiprocessing.Pool`` spawned per refresh,
+utils/model_utils.py:85-89); the loss is the squared distance of the matched pairs.
+
+Here the whole block stays on the GPU and inside the captured iteration:
+  * FPS of the canonical cloud and of every frame in ONE launch (``reart_fps``) -- computed once: both inputs are
+    constants of the optimisation and the CUDA kernel is deterministic (start index 0), so the reference's
+    per-refresh recomputation returns the same indices every time;
+  * ``reart_lap``: one CTA per frame solves the assignment exactly (shortest augmenting paths, float64 duals, costs
+    formed on the fly from the sampled points) -- no n x n matrix, no D2H, no host solver, no host sync;
+  * ``reart_assign_loss_grad``: matched-pair loss and its gradient into d loss / d skinned.
 """
 from __future__ import annotations
 
-from concurrent.futures import ThreadPoolExecutor
 from typing import Optional
 
-import numpy as np
 import torch
-from scipy.optimize import linear_sum_assignment
 
-from . import ops
+from . import _lib, ops
+from ._lib import check, ptr, stream_ptr
 
 
 def index_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
@@ -28,36 +33,98 @@ def farthest_point_sample(xyz: torch.Tensor, npoint: int) -> torch.Tensor:
     return ops.fps(xyz, npoint)
 
 
+@torch.no_grad()
+def lap_assign(src: torch.Tensor, tgt: torch.Tensor, src_idx: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+               want_total: bool = False, dual_u: Optional[torch.Tensor] = None, warm_start: bool = False):
+    """``[linear_sum_assignment(c) for c in torch.cdist(src_sampled, tgt)]`` on the GPU (include/reart_b200.h: reart_lap).
+
+    src [B,Ns,3] (source sample i is ``src[b, src_idx[i]]``; all Ns = n points when ``src_idx`` is None), tgt [B,n,3]
+    -> col4row [B,n] int32: the target matched to source sample i (scipy's ``col_ind``; its ``row_ind`` is arange).
+    With ``want_total`` also the float64 cost of each assignment.  ``dual_u`` [B,n] float64 receives the row duals; with
+    ``warm_start`` it also provides the starting duals (same optimum, far fewer augmentations after a small move).
+    n <= 4096."""
+    _lib.require_cuda(src, tgt, src_idx)
+    L = _lib.lib()
+    src = src.float().contiguous(); tgt = tgt.float().contiguous()
+    B, n = tgt.shape[0], tgt.shape[1]
+    if src_idx is not None:
+        src_idx = src_idx.to(torch.int64).contiguous()
+        assert src_idx.numel() == n
+    else:
+        assert src.shape[1] == n
+    col4row = out if out is not None else torch.empty(B, n, dtype=torch.int32, device=tgt.device)
+    assert col4row.dtype == torch.int32 and col4row.is_contiguous() and tuple(col4row.shape) == (B, n)
+    total = torch.empty(B, dtype=torch.float64, device=tgt.device) if want_total else None
+    if dual_u is not None:
+        assert dual_u.dtype == torch.float64 and dual_u.is_contiguous() and tuple(dual_u.shape) == (B, n)
+    with torch.cuda.device(tgt.device):
+        check(L.reart_lap(ptr(src), ptr(src_idx), src.shape[1], ptr(tgt), B, n, ptr(col4row), ptr(total), ptr(dual_u),
+                          1 if (warm_start and dual_u is not None) else 0, stream_ptr()), "reart_lap")
+    return (col4row, total) if want_total else col4row
+
+
 class AssignLoss:
-    """lambda_assign * sum ||src_matched - tgt_matched||^2 with assignments refreshed every ``assign_gap`` calls."""
+    """lambda_assign * sum ||src_matched - tgt_matched||^2 with assignments refreshed every ``assign_gap`` iterations.
+
+    ``solver="gpu"`` (default) is ``reart_lap``; ``solver="scipy"`` reproduces the reference's host path (cdist -> .cpu()
+    -> scipy) and exists for the parity tests and as the CPU-side timing baseline."""
 
     def __init__(self, cano_pc: torch.Tensor, pc_list: torch.Tensor, downsample: int = 4, assign_gap: int = 5,
-                 lambda_assign: float = 3e-1, workers: Optional[int] = None):
+                 lambda_assign: float = 3e-1, solver: str = "gpu"):
         self.cano_pc, self.pc_list = cano_pc, pc_list
-        self.T, N = pc_list.shape[0], pc_list.shape[1]
-        self.num_fps = N // downsample
-        self.assign_gap, self.lambda_assign = assign_gap, lambda_assign
+        self.T, self.N = pc_list.shape[0], pc_list.shape[1]
+        self.num_fps = self.N // downsample
+        if solver == "gpu" and self.num_fps > 4096:
+            raise _lib.ReartError(f"reart_lap handles n <= 4096 samples per frame; N / downsample = {self.num_fps}")
+        self.assign_gap, self.lambda_assign, self.solver = assign_gap, float(lambda_assign), solver
         self.calls = 0
-        # the sample indices never change (FPS is deterministic from index 0): compute them once
-        self.src_idx = farthest_point_sample(cano_pc[None], self.num_fps).expand(self.T, self.num_fps)
-        self.tgt_idx = farthest_point_sample(pc_list, self.num_fps)
-        self.pc_tgt = index_points(pc_list, self.tgt_idx)
-        self.pool = ThreadPoolExecutor(max_workers=workers or min(self.T, 16))
-        self.match_src = self.match_tgt = None
+        # the sample indices never change (FPS is deterministic from index 0, the clouds are constants): compute them once
+        self.src_idx = farthest_point_sample(cano_pc[None], self.num_fps)[0].contiguous()            # [n] (same for every frame)
+        self.tgt_idx = farthest_point_sample(pc_list, self.num_fps)                                  # [T,n]
+        self.pc_tgt = index_points(pc_list, self.tgt_idx).contiguous()                               # [T,n,3]
+        self.col4row = torch.zeros(self.T, self.num_fps, dtype=torch.int32, device=pc_list.device)
+        self.dual_u = torch.zeros(self.T, self.num_fps, dtype=torch.float64, device=pc_list.device)
+        self.have_assignment = False
 
-    def refresh(self, pc_src: torch.Tensor) -> None:
-        with torch.no_grad():
+    # ---------------------------------------------------------------------------------------------- refresh
+    @torch.no_grad()
+    def refresh(self, pc_trans_list: torch.Tensor) -> None:
+        """Solve the T assignments for the current skinned cloud [T,N,3] into ``self.col4row``."""
+        if self.solver == "gpu":
+            # zero duals = the cold start, so "warm" from the very first refresh keeps ONE captured flavour of the iteration
+            lap_assign(pc_trans_list.detach(), self.pc_tgt, self.src_idx, out=self.col4row, dual_u=self.dual_u, warm_start=True)
+        else:
+            import numpy as np
+            from scipy.optimize import linear_sum_assignment
+            pc_src = pc_trans_list.detach()[:, self.src_idx]
             cost = torch.cdist(pc_src, self.pc_tgt).cpu().numpy()
-        res = list(self.pool.map(linear_sum_assignment, cost))
-        dev = pc_src.device
-        self.match_src = torch.from_numpy(np.stack([r[0] for r in res])).to(dev)
-        self.match_tgt = torch.from_numpy(np.stack([r[1] for r in res])).to(dev)
+            cols = np.stack([linear_sum_assignment(c)[1] for c in cost]).astype(np.int32)
+            self.col4row.copy_(torch.from_numpy(cols))
+        self.have_assignment = True
+
+    def due(self, iteration: int, assign_iter: int = 0) -> bool:
+        """run_robot.py:165: refresh at the first assignment iteration and whenever ``i % assign_gap == 0``."""
+        return (not self.have_assignment) or iteration == assign_iter or iteration % self.assign_gap == 0
+
+    # ---------------------------------------------------------------------------------------------- autograd form
+    def loss(self, pc_trans_list: torch.Tensor) -> torch.Tensor:
+        """Differentiable matched-pair loss with the CURRENT assignment (run_robot.py:181-187)."""
+        a = pc_trans_list[:, self.src_idx]                                                            # [T,n,3]
+        b = index_points(self.pc_tgt, self.col4row.long())
+        return self.lambda_assign * ((a - b) ** 2).sum(dim=-1).sum()
 
     def __call__(self, pc_trans_list: torch.Tensor) -> torch.Tensor:
-        pc_src = index_points(pc_trans_list, self.src_idx)
-        if self.match_src is None or self.calls % self.assign_gap == 0:
-            self.refresh(pc_src.detach())
+        """Stand-alone use: refresh on the reference's schedule (counting calls), then the loss."""
+        if self.due(self.calls):
+            self.refresh(pc_trans_list)
         self.calls += 1
-        a = index_points(pc_src, self.match_src)
-        b = index_points(self.pc_tgt, self.match_tgt)
-        return self.lambda_assign * ((a - b) ** 2).sum(dim=-1).sum()
+        return self.loss(pc_trans_list)
+
+    # ---------------------------------------------------------------------------------------------- native form
+    def add_loss_and_grad(self, skinned: torch.Tensor, g_skinned: torch.Tensor, loss64: torch.Tensor, accumulate: bool) -> None:
+        """loss64 += lambda * sum |.|^2 ; g_skinned (+)= its gradient -- one launch, no autograd (engine native path)."""
+        L = _lib.lib()
+        with torch.cuda.device(skinned.device):
+            check(L.reart_assign_loss_grad(ptr(skinned), ptr(self.src_idx), ptr(self.pc_tgt), ptr(self.col4row), self.T, self.N,
+                                           self.num_fps, self.lambda_assign, ptr(g_skinned), 1 if accumulate else 0, ptr(loss64),
+                                           stream_ptr()), "reart_assign_loss_grad")

@@ -417,6 +417,26 @@ int reart_knn3_blend(const float* query, const float* ref_cat, const float* flow
                              static_cast<cudaStream_t>(stream_));
 }
 
+int reart_lap(const float* src, const int64_t* src_idx, int64_t src_points, const float* tgt, int64_t B, int64_t n,
+              int32_t* col4row, double* total, double* dual_u, int warm_start, void* stream_) {
+    if (B < 0 || n < 0 || src_points < 0) return REART_ERR_INVALID_ARG;
+    if (B == 0 || n == 0) return REART_OK;
+    if (!src || !tgt || !col4row || (!src_idx && src_points < n)) return REART_ERR_INVALID_ARG;
+    if (n > 4096) return REART_ERR_UNSUPPORTED;
+    return launch_lap(src, src_idx, src_points * 3, tgt, B, n, col4row, total, dual_u, warm_start && dual_u ? 1 : 0,
+                      static_cast<cudaStream_t>(stream_));
+}
+
+int reart_assign_loss_grad(const float* skinned, const int64_t* src_idx, const float* tgt, const int32_t* col4row, int64_t T,
+                           int64_t N, int64_t n, float lambda, float* g_skinned, int accumulate, double* loss,
+                           void* stream_) {
+    if (T < 0 || N < 0 || n < 0) return REART_ERR_INVALID_ARG;
+    if (T == 0 || n == 0) return REART_OK;
+    if (!skinned || !src_idx || !tgt || !col4row || !loss) return REART_ERR_INVALID_ARG;
+    return launch_assign_loss_grad(skinned, src_idx, tgt, col4row, T, N, n, lambda, g_skinned, accumulate, loss,
+                                   static_cast<cudaStream_t>(stream_));
+}
+
 int reart_fps(const float* xyz, int64_t B, int64_t N, int64_t npoint, int32_t* out, void* stream_) {
     if (B < 0 || N < 0 || npoint < 0) return REART_ERR_INVALID_ARG;
     if (B == 0 || npoint == 0) return REART_OK;

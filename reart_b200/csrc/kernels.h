@@ -130,6 +130,13 @@ int launch_segmlp(const float* x, const float* w0, const float* b0, const float*
 int launch_gumbel_st(const float* logits, const float* expo, const float* tau, const float* gW, int64_t N, int64_t P,
                      float* W, float* ysoft, float* glogits, cudaStream_t stream);
 
+// Assignment loss (lap.cu): exact linear sum assignment per frame on on-the-fly Euclidean costs + matched-pair loss/grad.
+int launch_lap(const float* src_base, const int64_t* src_idx, int64_t src_stride, const float* tgt, int64_t B, int64_t n,
+               int* col4row, double* total, double* dual_u, int warm, cudaStream_t stream);
+int launch_assign_loss_grad(const float* skinned, const int64_t* src_idx, const float* tgt, const int* col4row, int64_t T,
+                            int64_t N, int64_t n, float lambda, float* g_skinned, int accumulate, double* loss,
+                            cudaStream_t stream);
+
 // Fused frame-independent head / tail of one relaxation iteration (relax.cu).
 int launch_relax_head(const float* cano, const float* w0, const float* b0, const float* w2, const float* expo,
                       const float* tau, const float* d6, int64_t N, int64_t H, int64_t P, int64_t T, float* logits,

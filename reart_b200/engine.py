@@ -26,8 +26,7 @@ class _EngineBase:
     def __init__(self, ctx: Optional[DistContext], use_graph: bool):
         self.ctx = ctx or DistContext()
         self.use_graph = use_graph
-        self._graph = None
-        self._static_loss = None
+        self._graphs = {}
         self.iteration = 0
 
     # subclasses: _iteration() -> loss tensor (local part), self.optimizer, self.bucket
@@ -68,20 +67,28 @@ class _EngineBase:
     def _opt_params(self):
         return [p for g in self.optimizer.param_groups for p in g["params"]]
 
-    def _reset_optimizer_state(self):
-        for st in self.optimizer.state.values():
-            for v in st.values():
-                if torch.is_tensor(v):
-                    v.zero_()                                  # step, exp_avg, exp_avg_sq (kept in place)
+    def _opt_state_tensors(self):
+        return [v for st in self.optimizer.state.values() for v in st.values() if torch.is_tensor(v)]
 
-    def _capture(self):
+    def _aux_state_tensors(self):
+        """Other device state an iteration carries from step to step (restored after a capture's warm-up)."""
+        return []
+
+    def _variant(self):
+        """Which flavour of the iteration the NEXT step runs (hashable); one CUDA graph is captured per flavour."""
+        return None
+
+    def _capture(self, variant):
         """Warm up (allocator, library handles, NCCL communicator, lazily created Adam state), capture one
         iteration, then put parameters, optimiser state and the RNG stream back where they were, so a graph
-        run is step-for-step the same optimisation as an eager run."""
+        run is step-for-step the same optimisation as an eager run (also when a flavour is first needed mid-run)."""
         params = self._opt_params()
-        snapshot = [p.detach().clone() for p in params]
         dev = params[0].device
         rng_state = torch.cuda.get_rng_state(dev)
+        fresh_state = len(self._opt_state_tensors()) == 0          # torch creates Adam state lazily in the first step
+        snapshot = [p.detach().clone() for p in params]
+        opt_snapshot = [v.detach().clone() for v in self._opt_state_tensors()]
+        aux_snapshot = [v.detach().clone() for v in self._aux_state_tensors()]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -92,20 +99,26 @@ class _EngineBase:
         self.ctx.barrier()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self._static_loss = self._run_iteration()
-        self._graph = g
+            static_loss = self._run_iteration()
+        self._graphs[variant] = (g, static_loss)
         with torch.no_grad():
             for p, q in zip(params, snapshot):
                 p.copy_(q)
-            self._reset_optimizer_state()
+            if fresh_state:
+                for v in self._opt_state_tensors():
+                    v.zero_()                                  # step, exp_avg, exp_avg_sq (kept in place)
+            else:
+                for v, q in zip(self._opt_state_tensors(), opt_snapshot):
+                    v.copy_(q)
+            for v, q in zip(self._aux_state_tensors(), aux_snapshot):
+                v.copy_(q)
         torch.cuda.set_rng_state(rng_state, dev)
         torch.cuda.synchronize()
 
     def release(self) -> None:
-        """Drop the captured graph.  Must happen before the NCCL process group is destroyed: tearing down a
+        """Drop the captured graphs.  Must happen before the NCCL process group is destroyed: tearing down a
         communicator that a live CUDA graph still references blocks inside destroy_process_group()."""
-        self._graph = None
-        self._static_loss = None
+        self._graphs = {}
         torch.cuda.synchronize()
 
     def step(self, tau: Optional[float] = None) -> torch.Tensor:
@@ -113,12 +126,21 @@ class _EngineBase:
         if tau is not None:
             self.tau.fill_(float(tau))
         self.iteration += 1
+        variant = self._variant()
+        self._cur_variant = variant                            # fixed for this step (warm-up and capture included)
         if not self.use_graph:
-            return self._run_iteration()
-        if self._graph is None:
-            self._capture()
-        self._graph.replay()
-        return self._static_loss
+            out = self._run_iteration()
+            self._after_replay(variant)
+            return out
+        if variant not in self._graphs:
+            self._capture(variant)
+        g, static_loss = self._graphs[variant]
+        g.replay()
+        self._after_replay(variant)
+        return static_loss
+
+    def _after_replay(self, variant):
+        pass
 
 
 class RelaxationEngine(_EngineBase):
@@ -127,8 +149,12 @@ class RelaxationEngine(_EngineBase):
     def __init__(self, cano: torch.Tensor, frames: torch.Tensor, num_parts: int, ctx: Optional[DistContext] = None,
                  trans_lr: float = 1e-2, seg_lr: float = 1e-3, weight_decay: float = 0.0, use_graph: bool = True,
                  seed: int = 2, flow_ref=None, cano_idx: int = 0, lambda_flow: float = 1.0, robust_flow: bool = False,
-                 native: Optional[bool] = None, betas=(0.9, 0.999), eps: float = 1e-8):
-        """flow_ref: optional ``flow_utils.FlowReference`` (run_robot.py:78-84) enabling the flow loss of
+                 native: Optional[bool] = None, betas=(0.9, 0.999), eps: float = 1e-8, assign: Optional[dict] = None):
+        """assign: optional dict(downsample=4, assign_gap=5, lambda_assign=0.3, assign_iter=0, mode="add"|"replace")
+        enabling the assignment loss (run_robot.py:164-187): from iteration ``assign_iter`` on it is ADDED to the Chamfer
+        loss (run_real.py / run_sapien.py) or REPLACES it (run_robot.py's if/else); assignments are refreshed
+        on the GPU (``reart_lap``) at ``assign_iter`` and whenever ``i % assign_gap == 0``, inside the captured iteration.
+        flow_ref: optional ``flow_utils.FlowReference`` (run_robot.py:78-84) enabling the flow loss of
         run_robot.py:194-213.  Consecutive frames couple across shard boundaries: under frame sharding each rank
         receives one skinned frame per iteration from the previous rank (``dist.halo_from_previous_rank``)."""
         super().__init__(ctx, use_graph)
@@ -161,6 +187,15 @@ class RelaxationEngine(_EngineBase):
         self.pairs_per_step_local = 2 * (hi - lo) * self.cano.shape[0] * self.frames.shape[1]
         # recon-only iterations run on the fused head / energy / tail kernels with the library's own Adam (8 launches per
         # step, no autograd); extra losses on the skinned cloud (flow) keep the autograd composition
+        self.assign = None
+        if assign is not None:
+            from .assign import AssignLoss
+            cfg = dict(assign)
+            self.assign_iter = int(cfg.pop("assign_iter", 0))
+            self.assign_mode = cfg.pop("mode", "add")
+            if self.assign_mode not in ("add", "replace"):
+                raise ValueError("assign mode must be 'add' (run_real/run_sapien) or 'replace' (run_robot)")
+            self.assign = AssignLoss(self.cano, self.frames, **cfg)
         self.native = (flow_ref is None) if native is None else bool(native)
         if self.native:
             if flow_ref is not None:
@@ -230,12 +265,33 @@ class RelaxationEngine(_EngineBase):
             return [m.proposal_6d, m.proposal_t] + [q for q in m.seg_head.parameters() if q.requires_grad]
         return super()._opt_params()
 
-    def _reset_optimizer_state(self):
+    def _opt_state_tensors(self):
         if self.native:
-            for k in ("m_seg", "v_seg", "m_d6", "v_d6", "m_tr", "v_tr", "step"):
-                self._nat[k].zero_()
-            return
-        super()._reset_optimizer_state()
+            return [self._nat[k] for k in ("m_seg", "v_seg", "m_d6", "v_d6", "m_tr", "v_tr", "step")]
+        return super()._opt_state_tensors()
+
+    def _aux_state_tensors(self):
+        return [self.assign.col4row, self.assign.dual_u] if self.assign is not None else []
+
+    # ------------------------------------------------------------------------------------------ iteration flavours
+    def _phase(self):
+        """(use_chamfer, use_assign, refresh) of the iteration that is about to run (self.iteration is 1-based)."""
+        if self.assign is None:
+            return True, False, False
+        i = self.iteration - 1
+        if i < self.assign_iter:
+            return True, False, False
+        return self.assign_mode == "add", True, self.assign.due(i, self.assign_iter)
+
+    def _variant(self):
+        return self._phase()
+
+    def _after_replay(self, variant):
+        if variant[2]:
+            self.assign.have_assignment = True
+
+    def _step_phase(self):
+        return getattr(self, "_cur_variant", None) or self._phase()
 
     def _run_iteration_native(self):
         """head -> [memset, skin (x-sorted copy), search, energy columns, energy rows, skin backward, reduce] -> tail."""
@@ -247,15 +303,38 @@ class RelaxationEngine(_EngineBase):
         T, N, M, P, H = b["dims"]
         m = self.model
         conv0, conv2 = m.seg_head.model[0], m.seg_head.model[2]
+        use_chamfer, use_assign, refresh = self._step_phase()
         b["expo"].exponential_()                                  # the same RNG draw F.gumbel_softmax makes
         with torch.cuda.device(self.cano.device):
             check(L.reart_relax_head(ptr(self.cano), ptr(conv0.weight), ptr(conv0.bias), ptr(conv2.weight), ptr(b["expo"]),
                                      ptr(self.tau), ptr(m.proposal_6d), N, H, P, T, None, ptr(b["W"]), ptr(b["ysoft"]),
                                      ptr(b["R"]), stream_ptr()), "reart_relax_head")
-            check(L.reart_skinned_chamfer_fwd_bwd(ptr(self.cano), ptr(b["W"]), ptr(b["R"]), ptr(m.proposal_t), ptr(self.frames),
-                                                  ptr(self.frames_packed), T, N, M, P, ptr(b["skinned"]), ptr(b["loss64"]),
-                                                  ptr(b["gW"]), ptr(b["gR"]), ptr(b["gtr"]), None, 1, ptr(b["ws"]),
-                                                  b["ws_bytes"], stream_ptr()), "reart_skinned_chamfer_fwd_bwd")
+            if not use_assign:
+                check(L.reart_skinned_chamfer_fwd_bwd(ptr(self.cano), ptr(b["W"]), ptr(b["R"]), ptr(m.proposal_t), ptr(self.frames),
+                                                      ptr(self.frames_packed), T, N, M, P, ptr(b["skinned"]), ptr(b["loss64"]),
+                                                      ptr(b["gW"]), ptr(b["gR"]), ptr(b["gtr"]), None, 1, ptr(b["ws"]),
+                                                      b["ws_bytes"], stream_ptr()), "reart_skinned_chamfer_fwd_bwd")
+            else:
+                if "gs" not in b:
+                    b["gs"] = torch.zeros(T, N, 3, dtype=torch.float32, device=self.cano.device)
+                    b["bwd_ws_bytes"] = int(L.reart_skin_bwd_workspace_bytes(T, N, P))
+                    b["bwd_ws"] = _lib.workspace(b["bwd_ws_bytes"], self.cano.device)
+                if use_chamfer:                                   # Chamfer energy and its gradient w.r.t. the skinned cloud
+                    check(L.reart_skinned_chamfer_fwd_bwd(ptr(self.cano), ptr(b["W"]), ptr(b["R"]), ptr(m.proposal_t),
+                                                          ptr(self.frames), ptr(self.frames_packed), T, N, M, P, ptr(b["skinned"]),
+                                                          ptr(b["loss64"]), None, None, None, ptr(b["gs"]), 0, ptr(b["ws"]),
+                                                          b["ws_bytes"], stream_ptr()), "reart_skinned_chamfer_fwd_bwd")
+                else:                                             # run_robot.py:164-192: the assignment loss REPLACES Chamfer
+                    check(L.reart_skin_fwd(ptr(self.cano), ptr(b["W"]), ptr(b["R"]), ptr(m.proposal_t), T, N, P, ptr(b["skinned"]),
+                                           stream_ptr()), "reart_skin_fwd")
+                    b["gs"].zero_()
+                    b["loss64"].zero_()
+                if refresh:
+                    self.assign.refresh(b["skinned"])
+                self.assign.add_loss_and_grad(b["skinned"], b["gs"], b["loss64"], accumulate=True)
+                check(L.reart_skin_bwd(ptr(self.cano), ptr(b["W"]), ptr(b["R"]), ptr(m.proposal_t), ptr(b["gs"]), T, N, P,
+                                       ptr(b["gW"]), ptr(b["gR"]), ptr(b["gtr"]), ptr(b["bwd_ws"]), b["bwd_ws_bytes"], stream_ptr()),
+                      "reart_skin_bwd")
             a = b["args"]
             if not b["nccl"]:
                 check(L.reart_relax_tail(ctypes.byref(a), stream_ptr()), "reart_relax_tail")
@@ -269,9 +348,19 @@ class RelaxationEngine(_EngineBase):
         return b["loss_out"][0]
 
     def _iteration(self):
+        use_chamfer, use_assign, refresh = self._step_phase()
         seg, weight = self.model.weights(self.cano, tau=self.tau)
         R, tr = self.model.pose()
-        loss, skinned = ops.skinned_chamfer_loss(self.cano, weight, R, tr, self.frames, self.frames_packed, unit_grad=True)
+        if use_chamfer:
+            loss, skinned = ops.skinned_chamfer_loss(self.cano, weight, R, tr, self.frames, self.frames_packed,
+                                                     unit_grad=True)
+        else:
+            skinned = ops.skin(self.cano, weight, R, tr)
+            loss = skinned.new_zeros(())
+        if use_assign:
+            if refresh:
+                self.assign.refresh(skinned)
+            loss = loss + self.assign.loss(skinned)
         if self.flow_ref is not None:
             loss = loss + self.lambda_flow * self._flow_term(skinned)
         self.skinned = skinned.detach()                         # keep the cloud, not the autograd graph

@@ -60,9 +60,16 @@ def compute_ass_err(pc_trans_list: torch.Tensor, pc_list: torch.Tensor, use_npro
     """utils/model_utils.py:92-103 -- model-selection term (run_robot.py:306): mean squared distance of the optimal
     one-to-one matching between each posed cloud and its observed frame, (T,N,3) x2 -> scalar.
 
-    The Euclidean cost stays a torch op, the T Hungarian solves run on the host (scipy, as in the reference) in a
-    thread pool instead of a process pool spawned per call; the matched pairs are gathered on the device.
+    On CUDA with N <= 4096 the T assignments are solved on the GPU (``reart_lap``: exact, costs on the fly, no N x N
+    matrix and no D2H -- the reference copies T float64 N x N matrices to the host and runs scipy in a process pool);
+    otherwise the reference's host path (cdist -> scipy) in a thread pool.  ``use_nproc`` only matters on the host path.
     """
+    T, N = pc_list.shape[0], pc_list.shape[1]
+    if pc_list.is_cuda and N <= 4096:
+        from .assign import lap_assign
+        cols = lap_assign(pc_trans_list, pc_list).long()
+        b = torch.gather(pc_list, 1, cols[:, :, None].expand(-1, -1, 3))
+        return (pc_trans_list - b).square().sum(dim=-1).mean()
     import numpy as np
     from concurrent.futures import ThreadPoolExecutor
     from scipy.optimize import linear_sum_assignment

@@ -926,4 +926,18 @@ def test_candidate_fits_pick_the_lowest_energy_canonical_frame():
     # structure tail; a fit whose tree cannot be built scores +inf (the reference crashes there)
     best2, table2 = fit_candidates(cu(full), [0, 2, 4], num_parts=3, n_iter=60, use_graph=False)
     assert set(table2) == {0, 2, 4} and table2[best2] == min(table2.values())
-    assert any(np.isfinite(v) for v in table2.values())
+
+
+def test_candidate_energy_is_the_references_total_err(nao):
+    """engine.candidate_energy on the shipped base-2 relaxation checkpoint (nao demo) against the value the reference's own
+    functions give (tests/golden/total_err.npz, oracle/make_golden.py::gen_total_err): run_robot.py:224-240, 306-314."""
+    from reart_b200.engine import RelaxationEngine, candidate_energy
+    g, cano, pc_list = nao
+    gt = load_golden("total_err.npz")
+    eng = RelaxationEngine(cu(cano), cu(pc_list), num_parts=20, use_graph=False, native=False)
+    sd = {"proposal_6d": torch.from_numpy(g["katD_6d"]), "proposal_t": torch.from_numpy(g["katD_t"]),
+          "seg_head.model.0.weight": torch.from_numpy(g["katD_w0"]), "seg_head.model.0.bias": torch.from_numpy(g["katD_b0"]),
+          "seg_head.model.2.weight": torch.from_numpy(g["katD_w2"])}
+    eng.model.load_state_dict(sd, strict=False)
+    e = candidate_energy(eng, int(g["cano_idx"]))
+    assert abs(e - float(gt["total_err"])) <= 2e-3 * float(gt["total_err"]), (e, {k: float(gt[k]) for k in gt.files})
