@@ -424,12 +424,13 @@ def sweep_entry(workload, ctx, dev, flush, steps, warmup, peak_tf):
     import torch
     engine, _, _, T_total, N, P, desc = make_engine(workload, ctx, dev, True, "strong")
     ms, _, loss = time_engine_steps(engine, ctx, steps, warmup, flush)
+    final_loss = float(loss.item())                               # also surfaces any asynchronous error of the steps here
     k_ms, local_pairs, _ = search_kernel_timing(engine, flush, reps=3)
     n_ours, names = kernels_of_one_step(engine)
     pairs = 2.0 * T_total * N * N
     ent = {"workload": workload, "what": desc, "T": T_total, "N": N, "P": P, "steps": steps, "warmup": warmup,
            "ms_per_step": ms, "value": pairs / (ms * 1e-3), "unit": UNIT, "iters_per_s": 1e3 / ms,
-           "final_loss": float(loss.item()), "search_kernel_ms": k_ms,
+           "final_loss": final_loss, "search_kernel_ms": k_ms,
            "search_frac_of_fp32_peak": FLOP_PER_PAIR * local_pairs / (k_ms * 1e-3) / 1e12 / peak_tf,
            "our_kernels_per_step": n_ours,
            "kernels_per_step": {n[:70]: c for n, c in sorted(names.items(), key=lambda kv: -kv[1])}}
@@ -488,6 +489,11 @@ def main():
     T = WORKLOADS[args.workload][0]
     lo, hi = engine.frame_range
     frames_local_h = frames_h[lo:hi]
+    if getattr(engine, "perm_cano", None) is not None:
+        # the engine keeps both clouds in k-d leaf order (a one-time set-up step, like packing): the host copies that the
+        # e2e loop streams in every step are put into the same order once
+        cano_h = cano_h[engine.perm_cano.cpu()].pin_memory()
+        frames_local_h = torch.gather(frames_local_h, 1, engine.perm_frames.cpu()[:, :, None].expand(-1, -1, 3)).pin_memory()
     pairs_per_step = 2.0 * T_total * N * N
     uuid = str(torch.cuda.get_device_properties(dev).uuid)
 
@@ -546,6 +552,19 @@ def main():
     e2e_value = pairs_per_step / (float(t2.item()) * 1e-3)
     _ = float(host_loss)
 
+    culling = None
+    if getattr(engine, "cull", False) and hasattr(engine, "culling_stats"):
+        engine.culling_stats()                                    # reset, then measure over a few steady-state steps
+        for _ in range(5):
+            engine.step()
+        st = engine.culling_stats()
+        if st and st[1]:
+            culling = {"enabled": True, "block_pairs_evaluated": st[0], "block_pairs_offered": st[1],
+                       "fraction_evaluated": st[0] / st[1],
+                       "what": "exact tile culling (csrc/cull.cu): (256-row, 32-target) blocks whose bounding-box gap exceeds the "
+                               "upper bounds seeded by the previous step's arg-mins are skipped; results bit-identical to the "
+                               "brute-force search, which stays the kernel the roofline is quoted on"}
+
     # ---- roofline of the dominant kernel (chamfer_sym_kernel), timed alone with CUDA events on this stream
     Tl = hi - lo
     k_ms, local_pairs, alg_bytes = search_kernel_timing(engine, flush)
@@ -596,10 +615,11 @@ def main():
         if world == 1:
             for wl in SWEEP:
                 big = WORKLOADS[wl][1] >= 262144
-                try:
-                    sweep.append(sweep_entry(wl, ctx, dev, flush, 2 if big else 5, 3, peak_tf))
+                try:     # cfg2 refreshes its assignments every 5 steps: time enough steps to see the steady state
+                    sweep.append(sweep_entry(wl, ctx, dev, flush, 2 if big else (25 if wl == "cfg2" else 5), 3, peak_tf))
                 except Exception as exc:                          # never lose the headline line to a sweep failure
-                    sweep.append({"workload": wl, "error": f"{type(exc).__name__}: {exc}"})
+                    import traceback
+                    sweep.append({"workload": wl, "error": f"{type(exc).__name__}: {exc}", "traceback": traceback.format_exc()[-1500:]})
         else:
             try:
                 sweep.append(candidate_fits(ctx, dev))
@@ -629,7 +649,7 @@ def main():
                                        else "table (profiler unavailable)",
                 "step_kernels": {n[:70]: c for n, c in sorted(step_kernels.items(), key=lambda kv: -kv[1])},
                 "cuda_graph": not args.no_graph,
-                "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_reference_python": cpu_py,
+                "roofline": roofline, "culling": culling, "cpu_baseline": cpu, "cpu_baseline_reference_python": cpu_py,
                 "sustained": sustained, "sweep": sweep}
         print(json.dumps(line), flush=True)
     # teardown: captured graphs reference the NCCL communicator; with more than one rank leave through os._exit after

@@ -131,6 +131,21 @@ REART_API int reart_skinned_chamfer_fwd_bwd_ex(const float* cano, const float* W
                                             float* g_skinned, int compute_grad, float* d_fwd,
                                                int64_t* i_fwd, float* d_bwd, int64_t* i_bwd, void* workspace,
                                             int64_t workspace_bytes, void* stream);
+/* The same evaluation with EXACT tile culling (csrc/cull.cu, chamfer_sym.cu CULL): nn_rows [T,N] / nn_cols [T,M] int32
+ * carry the arg-mins from one call to the next (fill with -1 before the first call: that call is the brute-force
+ * search); they seed upper bounds of every minimum, and (256-row, 32-target) blocks whose bounding-box gap exceeds both
+ * bounds are skipped.  Loss, distances, indices and gradients are bit-identical to reart_skinned_chamfer_fwd_bwd_ex for
+ * ANY point order; how much is skipped depends on how spatially compact consecutive points are (engine.py sorts both
+ * clouds into k-d leaves once).  cull_stats (optional, device, [2] uint64, caller-zeroed): += (warp, chunk) pairs
+ * evaluated / offered.  Either nn pointer null: no culling. */
+REART_API int reart_skinned_chamfer_fwd_bwd_culled(const float* cano, const float* W, const float* R, const float* tr,
+                                                   const float* tgt, const float* tgt_packed, int64_t T, int64_t N,
+                                                   int64_t M, int64_t P, float* skinned, double* loss, float* gW,
+                                                   float* gR, float* gtr, float* g_skinned, int compute_grad,
+                                                   float* d_fwd, int64_t* i_fwd, float* d_bwd, int64_t* i_bwd,
+                                                   int32_t* nn_rows, int32_t* nn_cols, uint64_t* cull_stats,
+                                                   void* workspace, int64_t workspace_bytes, void* stream);
+
 
 /* ---------------------------------------------------------------------------------------------
  * Segmentation head and straight-through gumbel weights (the per-point, frame-independent part of an iteration).
@@ -155,16 +170,18 @@ REART_API int reart_gumbel_st_bwd(const float* ysoft, const float* tau, const fl
  * head: seg MLP forward (networks/blocks.py:99-118 via networks/model.py:42-43) + straight-through gumbel-softmax
  *       weights from caller-drawn Exponential(1) noise `expo` (F.gumbel_softmax(hard=True), networks/model.py:44)
  *       + 6D -> R (networks/model.py:60).  cano [N,3]; w0 [H,3], b0 [H], w2 [P,H]; expo [N,P]; tau [1]; d6 [T,P,6]
- *       -> logits [N,P] (optional), W [N,P], ysoft [N,P], R [T,P,3,3].
+ *       -> logits [N,P] (optional), W [N,P], ysoft [N,P], R [T,P,3,3].  noise_index [N] (optional): point n uses noise row
+ *       noise_index[n] -- for callers that reordered the cloud but want the random decisions of the original order.
  * tail: gumbel backward + seg MLP backward + 6D backward + (frames sharded over `world` ranks: the one-shot
  *       peer-memory all-reduce of reart_allreduce_oneshot, inline) + Adam with torch.optim.Adam semantics
  *       (run_robot.py:146-150, 219-221) on w0/b0/w2 (lr_seg) and d6/tr (lr_pose), all in ONE launch with a fixed
- *       summation order (bit-reproducible).  `tickets` [2] must be zero before the first call only.
+ *       summation order (bit-reproducible).  `tickets` [reart_relax_tail_ticket_words(N)] uint32 must be zero before the
+ *       first call only (the kernel re-arms them).
  *       phase 0: everything; phase 1: gradients -> bucket only (caller reduces the bucket, e.g. with NCCL);
  *       phase 2: Adam from the reduced bucket.
  * ------------------------------------------------------------------------------------------- */
 REART_API int reart_relax_head(const float* cano, const float* w0, const float* b0, const float* w2, const float* expo,
-                               const float* tau, const float* d6, int64_t N, int64_t H, int64_t P, int64_t T,
+                               const int64_t* noise_index, const float* tau, const float* d6, int64_t N, int64_t H, int64_t P, int64_t T,
                                float* logits, float* W, float* ysoft, float* R, void* stream);
 typedef struct reart_relax_tail_args {
     const float* cano;
@@ -185,6 +202,7 @@ typedef struct reart_relax_tail_args {
     int64_t N, H, P, T;
 } reart_relax_tail_args;
 REART_API int64_t reart_relax_tail_workspace_bytes(int64_t N, int64_t H, int64_t P);
+REART_API int64_t reart_relax_tail_ticket_words(int64_t N);
 REART_API int reart_relax_tail(const reart_relax_tail_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -39,6 +39,9 @@ SIGNATURES = {
                                                _vp, _vp, _vp, _vp, _c_int, _vp, _c_i64, _vp]),
     "reart_skinned_chamfer_fwd_bwd_ex": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _c_i64, _vp, _vp,
                                                   _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _c_i64, _vp]),
+    "reart_skinned_chamfer_fwd_bwd_culled": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _c_i64, _vp, _vp,
+                                                      _vp, _vp, _vp, _vp, _c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64,
+                                                      _vp]),
     "reart_segmlp_fwd": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp]),
     "reart_segmlp_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp, _vp]),
     "reart_gumbel_st_fwd": (_c_int, [_vp, _vp, _vp, _c_i64, _c_i64, _vp, _vp, _vp]),
@@ -72,8 +75,9 @@ class RelaxTailArgs(ctypes.Structure):
 
 
 SIGNATURES.update({
-    "reart_relax_head": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp, _vp, _vp]),
+    "reart_relax_head": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp, _vp, _vp]),
     "reart_relax_tail_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i64]),
+    "reart_relax_tail_ticket_words": (_c_i64, [_c_i64]),
     "reart_relax_tail": (_c_int, [ctypes.POINTER(RelaxTailArgs), _vp]),
     "reart_lap": (_c_int, [_vp, _vp, _c_i64, _vp, _c_i64, _c_i64, _vp, _vp, _vp, _c_int, _vp]),
     "reart_assign_loss_grad": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, ctypes.c_float, _vp, _c_int, _vp, _vp]),

@@ -70,7 +70,8 @@ class AssignLoss:
     -> scipy) and exists for the parity tests and as the CPU-side timing baseline."""
 
     def __init__(self, cano_pc: torch.Tensor, pc_list: torch.Tensor, downsample: int = 4, assign_gap: int = 5,
-                 lambda_assign: float = 3e-1, solver: str = "gpu"):
+                 lambda_assign: float = 3e-1, solver: str = "gpu", src_idx: Optional[torch.Tensor] = None,
+                 tgt_idx: Optional[torch.Tensor] = None):
         self.cano_pc, self.pc_list = cano_pc, pc_list
         self.T, self.N = pc_list.shape[0], pc_list.shape[1]
         self.num_fps = self.N // downsample
@@ -79,8 +80,9 @@ class AssignLoss:
         self.assign_gap, self.lambda_assign, self.solver = assign_gap, float(lambda_assign), solver
         self.calls = 0
         # the sample indices never change (FPS is deterministic from index 0, the clouds are constants): compute them once
-        self.src_idx = farthest_point_sample(cano_pc[None], self.num_fps)[0].contiguous()            # [n] (same for every frame)
-        self.tgt_idx = farthest_point_sample(pc_list, self.num_fps)                                  # [T,n]
+        # (src_idx / tgt_idx given: the caller sampled an equivalent cloud in another point order, e.g. the engine's k-d order)
+        self.src_idx = (farthest_point_sample(cano_pc[None], self.num_fps)[0] if src_idx is None else src_idx).contiguous()
+        self.tgt_idx = (farthest_point_sample(pc_list, self.num_fps) if tgt_idx is None else tgt_idx).contiguous()   # [T,n]
         self.pc_tgt = index_points(pc_list, self.tgt_idx).contiguous()                               # [T,n,3]
         self.col4row = torch.zeros(self.T, self.num_fps, dtype=torch.int32, device=pc_list.device)
         self.dual_u = torch.zeros(self.T, self.num_fps, dtype=torch.float64, device=pc_list.device)

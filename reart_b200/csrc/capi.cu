@@ -208,7 +208,8 @@ int64_t reart_energy_workspace_bytes(int64_t T, int64_t N, int64_t M) {
     return align_up(T * round_up(N, 256) * 12) + keys_bytes(T, N) + keys_bytes(T, M) + align_up(T * N * 12) +
            align_up(T * round_up(N, 256)) + align_up(xq_floats(T, round_up(N, 256)) * 4) +
            align_up(T * N * 24 + 64) + align_up(2 * (int64_t)energy_max_blocks() * 8) +
-           align_up(skin_bwd_workspace_floats(T, N, 32) * 4) + kAlign;
+           align_up(skin_bwd_workspace_floats(T, N, 32) * 4) + align_up(T * (padded_points(M) / kChunk) * 32) +
+           align_up(T * ceil_div(N, 256) * 4) + kAlign;
 }
 
 int reart_skinned_chamfer_fwd_bwd(const float* cano, const float* W, const float* R, const float* tr, const float* tgt,
@@ -224,6 +225,17 @@ int reart_skinned_chamfer_fwd_bwd_ex(const float* cano, const float* W, const fl
                                      double* loss, float* gW, float* gR, float* gtr, float* g_skinned, int compute_grad,
                                      float* d_fwd, int64_t* i_fwd, float* d_bwd, int64_t* i_bwd, void* workspace,
                                      int64_t workspace_bytes, void* stream_) {
+    return reart_skinned_chamfer_fwd_bwd_culled(cano, W, R, tr, tgt, tgt_packed, T, N, M, P, skinned, loss, gW, gR, gtr, g_skinned,
+                                                compute_grad, d_fwd, i_fwd, d_bwd, i_bwd, nullptr, nullptr, nullptr, workspace,
+                                                workspace_bytes, stream_);
+}
+
+int reart_skinned_chamfer_fwd_bwd_culled(const float* cano, const float* W, const float* R, const float* tr,
+                                         const float* tgt, const float* tgt_packed, int64_t T, int64_t N, int64_t M,
+                                         int64_t P, float* skinned, double* loss, float* gW, float* gR, float* gtr,
+                                         float* g_skinned, int compute_grad, float* d_fwd, int64_t* i_fwd, float* d_bwd,
+                                         int64_t* i_bwd, int32_t* nn_rows, int32_t* nn_cols, uint64_t* cull_stats,
+                                         void* workspace, int64_t workspace_bytes, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (T <= 0 || N <= 0 || M <= 0 || P <= 0 || P > 32 || !fits_int(T) || !fits_int(padded_points(N)) ||
         !fits_int(padded_points(M)))
@@ -244,6 +256,9 @@ int reart_skinned_chamfer_fwd_bwd_ex(const float* cano, const float* W, const fl
     char* zero = ws.take<char>(zero_bytes);
     double* partials = ws.take<double>(2 * (int64_t)energy_max_blocks());
     float* bwd_partials = compute_grad ? ws.take<float>(skin_bwd_workspace_floats(T, N, P)) : nullptr;
+    const bool cull = nn_rows != nullptr && nn_cols != nullptr;
+    float* colbox = cull ? ws.take<float>(T * (padded_points(M) / kChunk) * 8) : nullptr;
+    float* rowbound = cull ? ws.take<float>(T * ceil_div(N, 256)) : nullptr;
     if (!ws.ok) return REART_ERR_WORKSPACE;
     long long* acc = reinterpret_cast<long long*>(zero);
     unsigned* ticket = reinterpret_cast<unsigned*>(zero + T * N * 24);
@@ -255,6 +270,17 @@ int reart_skinned_chamfer_fwd_bwd_ex(const float* cano, const float* W, const fl
     sp.a = skinned; sp.b_packed = tgt_packed; sp.keys_a = ka; sp.keys_b = kb;
     sp.B = (int)T; sp.na = (int)N; sp.nb = (int)M; sp.nb_pad = (int)padded_points(M);
     sp.col_bound = col_bound;
+    if (cull) {
+        // seeds = the arg-mins of the previous evaluation (nn_* = -1: none, brute force); bounds, then the culled search
+        CullParams cp = {};
+        cp.a = skinned; cp.b = tgt; cp.nn_rows = nn_rows; cp.nn_cols = nn_cols;
+        cp.B = (int)T; cp.na = (int)N; cp.nb = (int)M; cp.nb_pad = (int)padded_points(M);
+        cp.colbox = colbox; cp.rowbound = rowbound;
+        rc = launch_cull_bounds(cp, stream);
+        if (rc) return rc;
+        sp.cull = 1; sp.colbox = colbox; sp.rowbound = rowbound;
+        sp.cull_stats = reinterpret_cast<unsigned long long*>(cull_stats);
+    }
     rc = launch_chamfer_sym(sp, stream);
     if (rc) return rc;
     EnergyParams ep = {};
@@ -263,6 +289,7 @@ int reart_skinned_chamfer_fwd_bwd_ex(const float* cano, const float* W, const fl
     ep.row_chunk_pts = kChunk; ep.col_chunk_pts = sp.col_chunk_pts; ep.gscale = 1.0f; ep.g_src = gs; ep.loss = loss;
     if (sp.col_chunk_pts != 256) return REART_ERR_UNSUPPORTED;       // the sorted copy is built per 256-point chunk
     ep.d_fwd = d_fwd; ep.i_fwd = i_fwd; ep.d_bwd = d_bwd; ep.i_bwd = i_bwd;
+    ep.nn_rows = nn_rows; ep.nn_cols = nn_cols;                      // the next evaluation's seeds
     ep.src_perm = perm; ep.src_xq = xq; ep.acc = acc; ep.col_bound = col_bound; ep.partials = partials; ep.ticket = ticket;
     rc = launch_energy_bwd(ep, stream);
     if (rc || !compute_grad) return rc;
@@ -310,12 +337,12 @@ int reart_gumbel_st_bwd(const float* ysoft, const float* tau, const float* gW, i
 }
 
 int reart_relax_head(const float* cano, const float* w0, const float* b0, const float* w2, const float* expo,
-                     const float* tau, const float* d6, int64_t N, int64_t H, int64_t P, int64_t T, float* logits,
+                     const int64_t* noise_index, const float* tau, const float* d6, int64_t N, int64_t H, int64_t P, int64_t T, float* logits,
                      float* W, float* ysoft, float* R, void* stream_) {
     if (N < 0 || T < 0 || H <= 0 || P <= 0 || !fits_int(4 * N) || !fits_int(T * P)) return REART_ERR_INVALID_ARG;
     if (N > 0 && (!cano || !w0 || !b0 || !w2 || !expo || !tau || !W || !ysoft)) return REART_ERR_INVALID_ARG;
     if (T > 0 && (!d6 || !R)) return REART_ERR_INVALID_ARG;
-    return launch_relax_head(cano, w0, b0, w2, expo, tau, d6, N, H, P, T, logits, W, ysoft, R,
+    return launch_relax_head(cano, w0, b0, w2, expo, noise_index, tau, d6, N, H, P, T, logits, W, ysoft, R,
                              static_cast<cudaStream_t>(stream_));
 }
 
@@ -323,6 +350,8 @@ int64_t reart_relax_tail_workspace_bytes(int64_t N, int64_t H, int64_t P) {
     if (N < 0 || H <= 0 || P <= 0) return -1;
     return align_up(relax_tail_workspace_floats(N, H, P) * 4) + kAlign;
 }
+
+int64_t reart_relax_tail_ticket_words(int64_t N) { return N < 0 ? -1 : relax_tail_ticket_words(N); }
 
 int reart_relax_tail(const reart_relax_tail_args* x, void* stream_) {
     if (!x || x->N <= 0 || x->T <= 0 || x->H <= 0 || x->P <= 0 || !fits_int(x->N) || !fits_int(x->T * x->P))

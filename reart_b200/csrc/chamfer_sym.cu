@@ -44,13 +44,21 @@ struct SymCfg {
     static constexpr int kColChunkPts = 32 * R / S;
 };
 
-template <int R, int S>
+// CULL = true adds the exact tile culling of DESIGN.md section 4.4: every 32-target chunk arrives with its bounding box
+// and an upper bound of its columns' final minima (cull.cu), every warp knows the box of its 256 rows and an upper bound
+// of their final minima; a (warp, chunk) pair whose box-to-box squared gap -- formed with the same subtract / multiply /
+// fma sequence as a point distance, hence a lower bound of every computed pair distance -- is STRICTLY larger than both
+// bounds cannot contain a minimum or a tie of either side and is skipped.  Keys are bit-identical to the brute force.
+constexpr int kBoxFloats = 8;                                  // lo.xyz, hi.xyz, column bound, pad  (32 B per chunk)
+
+template <int R, int S, bool CULL>
 __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymParams p) {
     using C = SymCfg<R, S>;
     constexpr int RS = R / S;                                  // points per lane per sub-chunk
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // [stages][tile bytes] | [2][warps][S][tile points] u32
+    // [stages][tile bytes] | [2][warps][S][tile points] u32 | CULL: [stages][tile chunks][8] f32 boxes
     unsigned* colmin = reinterpret_cast<unsigned*>(smem_raw + kSymStages * C::kTileBytes);
+    float* sbox = reinterpret_cast<float*>(smem_raw + C::kSmem);
     __shared__ __align__(8) uint64_t full_bar[kSymStages];
 
     int item = blockIdx.x;
@@ -68,13 +76,32 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymPa
     u64 QX[R], QY[R], QZ[R];
     float best[R], prev[R];
     unsigned bch[R];
+    float rlx = INFINITY, rly = INFINITY, rlz = INFINITY, rhx = -INFINITY, rhy = -INFINITY, rhz = -INFINITY;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int i = qbase + warp * (32 * R) + (r / RS) * (32 * RS) + lane * RS + (r % RS);
         float x = INFINITY, y = INFINITY, z = INFINITY;          // out-of-range rows never win a column
-        if (i < p.na) { x = q[3 * i]; y = q[3 * i + 1]; z = q[3 * i + 2]; }
+        if (i < p.na) {
+            x = q[3 * i]; y = q[3 * i + 1]; z = q[3 * i + 2];
+            if (CULL) {
+                rlx = fminf(rlx, x); rly = fminf(rly, y); rlz = fminf(rlz, z);
+                rhx = fmaxf(rhx, x); rhy = fmaxf(rhy, y); rhz = fmaxf(rhz, z);
+            }
+        }
         QX[r] = pack2(x, x); QY[r] = pack2(y, y); QZ[r] = pack2(z, z);
         best[r] = INFINITY; prev[r] = INFINITY; bch[r] = 0u;
+    }
+    float rbound = INFINITY;                                   // upper bound of the final minima of this warp's rows
+    unsigned evaluated = 0u;
+    if (CULL) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            rlx = fminf(rlx, __shfl_xor_sync(0xffffffffu, rlx, o)); rly = fminf(rly, __shfl_xor_sync(0xffffffffu, rly, o));
+            rlz = fminf(rlz, __shfl_xor_sync(0xffffffffu, rlz, o)); rhx = fmaxf(rhx, __shfl_xor_sync(0xffffffffu, rhx, o));
+            rhy = fmaxf(rhy, __shfl_xor_sync(0xffffffffu, rhy, o)); rhz = fmaxf(rhz, __shfl_xor_sync(0xffffffffu, rhz, o));
+        }
+        const int rc = qbase / (32 * R) + warp;                // this warp's 256-row chunk
+        if (rc * (32 * R) < p.na) rbound = __ldg(p.rowbound + (int64_t)b * p.row_chunks + rc);
     }
 
     const int chunks_total = p.nb_pad / kChunk;
@@ -95,12 +122,17 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymPa
 
     unsigned cmax = 0u;                                      // largest finite column minimum this thread merged
 
+    const float* __restrict__ bp = CULL ? p.colbox + ((int64_t)b * chunks_total + chunk0) * kBoxFloats : nullptr;
     auto issue = [&](int k) {
         const int st = k % kSymStages;
         const int nch = min(C::kTileChunks, nchunks - k * C::kTileChunks);
         const uint32_t bytes = (uint32_t)nch * kChunk * 12;
-        mbar_expect_tx(&full_bar[st], bytes);
+        const uint32_t box_bytes = CULL ? (uint32_t)nch * kBoxFloats * 4 : 0u;
+        mbar_expect_tx(&full_bar[st], bytes + box_bytes);
         tma_bulk_g2s(smem_raw + st * C::kTileBytes, tp + (int64_t)k * C::kTilePoints * 3, bytes, &full_bar[st]);
+        if (CULL)
+            tma_bulk_g2s(sbox + st * C::kTileChunks * kBoxFloats, bp + (int64_t)k * C::kTileChunks * kBoxFloats, box_bytes,
+                         &full_bar[st]);
     };
     if (tid == 0) {
         for (int k = 0; k < min(kSymStages, ntiles); ++k) issue(k);
@@ -114,6 +146,27 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymPa
         unsigned* __restrict__ cbuf = colmin + (k & 1) * C::kColBufWords;
         unsigned* __restrict__ cm_w = cbuf + warp * (S * C::kTilePoints);
         for (int c = 0; c < nch; ++c) {
+            if (CULL) {
+                const float4 b0 = *reinterpret_cast<const float4*>(sbox + (st * C::kTileChunks + c) * kBoxFloats);
+                const float4 b1 = *reinterpret_cast<const float4*>(sbox + (st * C::kTileChunks + c) * kBoxFloats + 4);
+                // b0 = (lo.x, lo.y, lo.z, hi.x), b1 = (hi.y, hi.z, column bound, -)
+                const float gx = fmaxf(0.f, fmaxf(__fsub_rn(rlx, b0.w), __fsub_rn(b0.x, rhx)));
+                const float gy = fmaxf(0.f, fmaxf(__fsub_rn(rly, b1.x), __fsub_rn(b0.y, rhy)));
+                const float gz = fmaxf(0.f, fmaxf(__fsub_rn(rlz, b1.y), __fsub_rn(b0.z, rhz)));
+                const float lb = __fmaf_rn(gz, gz, __fmaf_rn(gy, gy, __fmul_rn(gx, gx)));
+                if (lb > rbound && lb > b1.z) {                // warp-uniform: no minimum and no tie of either side in here
+                    if (lane == 0) {
+                        const uint4 inf4 = make_uint4(0x7f800000u, 0x7f800000u, 0x7f800000u, 0x7f800000u);
+#pragma unroll
+                        for (int s = 0; s < S; ++s)
+#pragma unroll
+                            for (int g = 0; g < kChunk / 4; ++g)
+                                *reinterpret_cast<uint4*>(cm_w + s * C::kTilePoints + c * kChunk + 4 * g) = inf4;
+                    }
+                    continue;
+                }
+                ++evaluated;
+            }
             const float4* __restrict__ cg = tile + c * (kChunk / 4 * 3);
 #pragma unroll
             for (int g = 0; g < kChunk / 4; ++g) {
@@ -176,6 +229,10 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymPa
         // only after finishing this fold
     }
 
+    if (CULL && p.cull_stats && lane == 0) {                  // (warp, chunk) pairs evaluated / offered: the culling rate
+        atomicAdd(p.cull_stats, (unsigned long long)evaluated);
+        atomicAdd(p.cull_stats + 1, (unsigned long long)max(nchunks, 0));
+    }
     if (p.col_bound) {                                       // one atomic per warp: bound for the fixed-point energy scatter
         cmax = __reduce_max_sync(0xffffffffu, cmax);
         if (lane == 0 && cmax) atomicMax(p.col_bound, cmax);
@@ -223,7 +280,7 @@ static int sym_choose_splits(int64_t B, int qblocks, int chunks_total, int tile_
     return best_s;
 }
 
-template <int R, int S>
+template <int R, int S, bool CULL>
 static int launch_sym_rs(SymParams& p, cudaStream_t stream) {
     using C = SymCfg<R, S>;
     p.qblocks = (int)ceil_div(p.na, R * kSymThreads);
@@ -250,11 +307,13 @@ static int launch_sym_rs(SymParams& p, cudaStream_t stream) {
     int devid = 0;
     cudaGetDevice(&devid);
     if (devid < 0 || devid >= 64 || !attr_done[devid]) {
-        if (cudaFuncSetAttribute(chamfer_sym_kernel<R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem) != cudaSuccess)
+        if (cudaFuncSetAttribute(chamfer_sym_kernel<R, S, CULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(C::kSmem + kSymStages * C::kTileChunks * kBoxFloats * 4)) != cudaSuccess)
             return kErrLaunch;
         if (devid >= 0 && devid < 64) attr_done[devid] = true;
     }
-    chamfer_sym_kernel<R, S><<<(unsigned)items, kSymThreads, C::kSmem, stream>>>(p);
+    const size_t smem = C::kSmem + (CULL ? (size_t)kSymStages * C::kTileChunks * kBoxFloats * 4 : 0);
+    chamfer_sym_kernel<R, S, CULL><<<(unsigned)items, kSymThreads, smem, stream>>>(p);
     REART_CHECK_LAUNCH();
     return kOk;
 }
@@ -263,11 +322,16 @@ int launch_chamfer_sym(SymParams& p, cudaStream_t stream) {
     // Measured on B200 (profiles/r01_sym_variants.log, T=64 x 16k): S=1 3.70 ms, S=2 3.87, S=4 4.17, S=8 4.45 --
     // one REDUX per target (S=1, 256-point column chunks) is the fastest search even after paying for the wider
     // index recovery (which the x-sorted packed copy makes cheap, skin.cu / energy.cu).
+    if (p.cull) {
+        if (!p.colbox || !p.rowbound) return kErrInvalidArg;
+        p.row_chunks = (int)ceil_div(p.na, 256);
+        return launch_sym_rs<8, 1, true>(p, stream);
+    }
     switch (p.variant % 16) {
-        case 2: return launch_sym_rs<8, 2>(p, stream);
-        case 4: return launch_sym_rs<8, 4>(p, stream);
-        case 8: return launch_sym_rs<8, 8>(p, stream);
-        default: return launch_sym_rs<8, 1>(p, stream);
+        case 2: return launch_sym_rs<8, 2, false>(p, stream);
+        case 4: return launch_sym_rs<8, 4, false>(p, stream);
+        case 8: return launch_sym_rs<8, 8, false>(p, stream);
+        default: return launch_sym_rs<8, 1, false>(p, stream);
     }
 }
 

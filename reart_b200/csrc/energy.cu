@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(kEnergyThreads) energy_cols_kernel(const Energ
         local += (double)dmin;
         if (p.d_bwd) p.d_bwd[f] = dmin;
         if (p.i_bwd) p.i_bwd[f] = i;
+        if (p.nn_cols) p.nn_cols[f] = i;
     }
     const double s = block_sum(local, sh);
     if (threadIdx.x == 0) p.partials[blockIdx.x] = s;
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(kEnergyThreads) energy_rows_kernel(const Energ
         local += (double)dmin;
         if (p.d_fwd) p.d_fwd[e] = dmin;
         if (p.i_fwd) p.i_fwd[e] = j;
+        if (p.nn_rows) p.nn_rows[e] = j;
     }
     const double s = block_sum(local, sh);
     if (threadIdx.x == 0) {

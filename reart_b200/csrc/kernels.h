@@ -43,7 +43,23 @@ struct SymParams {
     int variant;                  // 0 = default; 1/2/4/8 = number of column sub-chunks per warp (tuning)
     unsigned* col_bound;          // null, or one word (zero on entry): atomicMax of the finite column minima every CTA
                                   // saw, as float bits -- an upper bound of every final column minimum (energy.cu)
+    // exact tile culling (cull.cu builds these; chamfer_sym.cu CULL = true consumes them)
+    int cull;                     // 1: use the culled schedule
+    const float* colbox;          // [B, nb_pad/32, 8]: lo.xyz, hi.xyz of the chunk's real points, upper bound of its columns' minima, pad
+    const float* rowbound;        // [B, ceil(na/256)]: upper bound of the final minima of each 256-row chunk
+    int row_chunks;               // filled by the launcher
+    unsigned long long* cull_stats;   // null, or [2] (zero on entry): (warp, chunk) pairs evaluated / offered
 };
+struct CullParams {
+    const float* a;               // [B,na,3] rows (skinned cloud)
+    const float* b;               // [B,nb,3] columns (observed frames)
+    const int32_t* nn_rows;       // [B,na] arg-min column of every row from an EARLIER evaluation, -1: unknown
+    const int32_t* nn_cols;       // [B,nb] arg-min row of every column, -1: unknown
+    int B, na, nb, nb_pad;
+    float* colbox;                // out [B, nb_pad/32, 8]
+    float* rowbound;              // out [B, ceil(na/256)]
+};
+int launch_cull_bounds(const CullParams& p, cudaStream_t stream);
 
 int launch_pack_cloud(const float* pts, float* packed, int64_t B, int64_t P, cudaStream_t stream);
 int launch_pack_cloud_sorted(const float* pts, float* packed, unsigned char* perm, float* xq, int64_t B, int64_t P,
@@ -110,6 +126,7 @@ struct EnergyParams {
     const unsigned* col_bound;    // [1] float bits >= every column minimum (SymParams::col_bound)
     double* partials;             // [2 * energy_max_blocks()] per-block loss partials (no initialisation needed)
     unsigned* ticket;             // [1] ZERO on entry
+    int32_t* nn_rows; int32_t* nn_cols;   // optional [B,N] / [B,M]: the arg-mins, kept as the next evaluation's culling seeds
     float* d_fwd; int64_t* i_fwd; // optional [B,N]
     float* d_bwd; int64_t* i_bwd; // optional [B,M]
 };
@@ -139,7 +156,7 @@ int launch_assign_loss_grad(const float* skinned, const int64_t* src_idx, const 
 
 // Fused frame-independent head / tail of one relaxation iteration (relax.cu).
 int launch_relax_head(const float* cano, const float* w0, const float* b0, const float* w2, const float* expo,
-                      const float* tau, const float* d6, int64_t N, int64_t H, int64_t P, int64_t T, float* logits,
+                      const int64_t* noise_index, const float* tau, const float* d6, int64_t N, int64_t H, int64_t P, int64_t T, float* logits,
                       float* W, float* ysoft, float* R, cudaStream_t stream);
 struct RelaxTail {
     const float* cano;            // [N,3]
@@ -154,7 +171,7 @@ struct RelaxTail {
     float* step;                  // [1] completed optimisation steps (advanced by the kernel)
     float lr_pose, lr_seg, beta1, beta2, eps, wd;
     float* partials;              // [ceil(N/128)][4H + PH] per-chunk seg-gradient partials
-    unsigned* tickets;            // [2] zero before the FIRST call; the kernel re-arms them itself
+    unsigned* tickets;            // [relax_tail_ticket_words(N)] zero before the FIRST call; the kernel re-arms them itself
     const double* loss_local;     // [1] this rank's loss
     float* bucket;                // [4H + PH + 1] reduced seg gradients + loss
     float* loss_out;              // [1] all-rank loss of the step
@@ -163,6 +180,7 @@ struct RelaxTail {
     int N, H, P, T;
 };
 int64_t relax_tail_workspace_floats(int64_t N, int64_t H, int64_t P);
+int64_t relax_tail_ticket_words(int64_t N);
 int launch_relax_tail(const RelaxTail& a, cudaStream_t stream);
 
 int launch_allreduce_oneshot(const unsigned long long* peer_base, int rank, int world, int64_t n, int64_t n_pad,

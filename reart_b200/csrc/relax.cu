@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(kHeadThreads) relax_head_kernel(const float* _
                                                                   const float* __restrict__ b0,
                                                                   const float* __restrict__ w2,
                                                                   const float* __restrict__ expo,
+                                                                  const int64_t* __restrict__ noise_index,
                                                                   const float* __restrict__ tau_ptr,
                                                                   const float* __restrict__ d6, int N, int H, int P,
                                                                   int TP, int point_blocks, float* __restrict__ logits,
@@ -82,12 +83,15 @@ __global__ void __launch_bounds__(kHeadThreads) relax_head_kernel(const float* _
     if (!real) return;
     // straight-through gumbel softmax: every lane of the point evaluates the (tiny) softmax, each writes its parts
     const float inv_tau = 1.0f / *tau_ptr;
+    // noise row of this point: its own, or (point order changed by the caller, e.g. the engine's k-d order) the row the
+    // point had in the order the noise was drawn for -- the optimisation then takes the same random decisions
+    const int64_t nrow = noise_index ? noise_index[n] : (int64_t)n;
     float z[PMAX];
     float mx = -INFINITY;
 #pragma unroll
     for (int p = 0; p < PMAX; ++p) {
         if (p < P) {
-            z[p] = (acc[p] - logf(expo[(int64_t)n * P + p])) * inv_tau;
+            z[p] = (acc[p] - logf(expo[nrow * P + p])) * inv_tau;
             mx = fmaxf(mx, z[p]);
         }
     }
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(kHeadThreads) relax_head_kernel(const float* _
 }
 
 int launch_relax_head(const float* cano, const float* w0, const float* b0, const float* w2, const float* expo,
-                      const float* tau, const float* d6, int64_t N, int64_t H, int64_t P, int64_t T, float* logits,
+                      const int64_t* noise_index, const float* tau, const float* d6, int64_t N, int64_t H, int64_t P, int64_t T, float* logits,
                       float* W, float* ysoft, float* R, cudaStream_t stream) {
     if (N <= 0 && T <= 0) return kOk;
     if (H <= 0 || H > 1024 || P <= 0 || P > 32) return kErrUnsupported;
@@ -123,7 +127,7 @@ int launch_relax_head(const float* cano, const float* w0, const float* b0, const
         const size_t smem = (size_t)H * (4 + PM) * sizeof(float);                                                    \
         if (smem > 48 * 1024) return kErrUnsupported;                                                                \
         relax_head_kernel<PM><<<(unsigned)(point_blocks + pose_blocks), kHeadThreads, smem, stream>>>(               \
-            cano, w0, b0, w2, expo, tau, d6, (int)N, (int)H, (int)P, (int)(T * P), point_blocks, logits, W, ysoft, R); \
+            cano, w0, b0, w2, expo, noise_index, tau, d6, (int)N, (int)H, (int)P, (int)(T * P), point_blocks, logits, W, ysoft, R); \
     } while (0)
     if (P <= 8) REART_HEAD(8);
     else if (P <= 16) REART_HEAD(16);
@@ -135,6 +139,7 @@ int launch_relax_head(const float* cano, const float* w0, const float* b0, const
 
 // ============================================================================================ tail
 constexpr int kTailPoints = 128;                             // points per block (seg-MLP backward chunk)
+constexpr int kTailGroup = 8;                                // chunks per first-level reduction group
 
 // torch.optim.Adam (no amsgrad), one element: exp_avg.lerp_(g, 1-b1); exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2);
 // p -= (lr / bc1) * exp_avg / (sqrt(exp_avg_sq) / sqrt(bc2) + eps)        (torch/optim/adam.py, _fused_adam math)
@@ -210,7 +215,7 @@ __device__ bool cta_allreduce_oneshot(const unsigned long long* __restrict__ pee
 template <int PMAX>
 __global__ void __launch_bounds__(1024) relax_tail_kernel(const RelaxTail a, int point_blocks, int Hpad) {
     extern __shared__ __align__(16) float sm[];
-    __shared__ bool last_pts;
+    __shared__ bool last_pts, last_grp;
     __shared__ int s_ok;
     const int tid = threadIdx.x;
     const int H = a.H, P = a.P;
@@ -324,33 +329,65 @@ __global__ void __launch_bounds__(1024) relax_tail_kernel(const RelaxTail a, int
                 if (p < P) out[4 * H + p * H + k] = a2[p];
         }
         __syncthreads();
+        // ---- two-level fixed-order reduction of the per-chunk partials (a single last block summing all of them is a
+        // chain of ~80 dependent L2 round trips at 128 chunks: 40 us).  Level 1: the last of each group of kTailGroup
+        // consecutive chunks adds the group's partials in chunk order; level 2: the last group adds the group sums in
+        // group order.  Both orders are fixed, so the bucket is bit-reproducible.
+        const int ngroups = (point_blocks + kTailGroup - 1) / kTailGroup;
+        const int grp = (int)blockIdx.x / kTailGroup;
+        const int g0 = grp * kTailGroup, gn = min(kTailGroup, point_blocks - g0);
+        float* gpart = a.partials + (int64_t)point_blocks * nseg;             // [ngroups][nseg]
         if (tid == 0) {
             __threadfence();
-            last_pts = atomicAdd(a.tickets, 1u) == (unsigned)point_blocks - 1u;
+            last_grp = atomicAdd(a.tickets + 2 + grp, 1u) == (unsigned)gn - 1u;
         }
         __syncthreads();
-        if (last_pts) {
-            // ---- the last chunk to finish: partials -> bucket in chunk order, then [all-reduce], then Adam
+        last_pts = false;
+        if (last_grp) {
             __threadfence();
-            // eight independent running sums per output (chunks c = i mod 8, in order), combined in a fixed order:
-            // L2 loads (ld.cg: the partials were written by other CTAs) stay eight deep in flight
-            const float* part = a.partials;
+            const float* part = a.partials + (int64_t)g0 * nseg;
             for (int e = tid; e < nseg; e += blockDim.x) {
-                float s8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                int c = 0;
-                for (; c + 8 <= point_blocks; c += 8) {
+                float v[kTailGroup];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) s8[i] += __ldcg(part + (int64_t)(c + i) * nseg + e);
+                for (int c = 0; c < kTailGroup; ++c) v[c] = c < gn ? __ldcg(part + (int64_t)c * nseg + e) : 0.f;
+                float sacc = v[0];
+#pragma unroll
+                for (int c = 1; c < kTailGroup; ++c) sacc += v[c];
+                gpart[(int64_t)grp * nseg + e] = sacc;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                last_pts = atomicAdd(a.tickets, 1u) == (unsigned)ngroups - 1u;
+            }
+            __syncthreads();
+        }
+        if (last_pts) {
+            // ---- the last group to finish: group sums -> bucket in group order, then [all-reduce], then Adam
+            __threadfence();
+            for (int e = tid; e < nseg; e += blockDim.x) {
+                float sacc = 0.f;
+                int c = 0;
+                for (; c + 8 <= ngroups; c += 8) {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = __ldcg(gpart + (int64_t)(c + i) * nseg + e);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) sacc += v[i];
                 }
-                for (int i = 0; c < point_blocks; ++c, ++i) s8[i] += __ldcg(part + (int64_t)c * nseg + e);
-                a.bucket[e] = ((s8[0] + s8[1]) + (s8[2] + s8[3])) + ((s8[4] + s8[5]) + (s8[6] + s8[7]));
+                for (; c < ngroups; ++c) sacc += __ldcg(gpart + (int64_t)c * nseg + e);
+                a.bucket[e] = sacc;
             }
             if (tid == 0) a.bucket[nseg] = (float)*reinterpret_cast<const volatile double*>(a.loss_local);
             __syncthreads();
         }
     }
     if (a.phase == 1) {                                        // reduce only: the caller all-reduces the bucket (NCCL)
-        if ((int)blockIdx.x < point_blocks && last_pts && tid == 0) *a.tickets = 0u;
+        if ((int)blockIdx.x < point_blocks && last_pts) {       // re-arm the point-side tickets for the next launch
+            const int ngroups = (point_blocks + kTailGroup - 1) / kTailGroup;
+            for (int e = tid; e < ngroups; e += blockDim.x) a.tickets[2 + e] = 0u;
+            if (tid == 0) a.tickets[0] = 0u;
+        }
         return;
     }
     const bool seg_owner = a.phase == 2 ? (blockIdx.x == 0) : ((int)blockIdx.x < point_blocks && last_pts);
@@ -370,13 +407,18 @@ __global__ void __launch_bounds__(1024) relax_tail_kernel(const RelaxTail a, int
         __threadfence();
         if (atomicAdd(a.tickets + 1, 1u) == gridDim.x - 1u) {
             *a.step = step;
-            a.tickets[0] = 0u; a.tickets[1] = 0u;
+            const int ngroups = (point_blocks + kTailGroup - 1) / kTailGroup;
+            for (int e = 0; e < 2 + ngroups; ++e) a.tickets[e] = 0u;
         }
     }
 }
 
 int64_t relax_tail_workspace_floats(int64_t N, int64_t H, int64_t P) {
-    return ceil_div(N > 0 ? N : 1, kTailPoints) * (4 * H + P * H);
+    const int64_t blocks = ceil_div(N > 0 ? N : 1, kTailPoints);
+    return (blocks + ceil_div(blocks, kTailGroup)) * (4 * H + P * H);
+}
+int64_t relax_tail_ticket_words(int64_t N) {
+    return 2 + ceil_div(ceil_div(N > 0 ? N : 1, kTailPoints), kTailGroup);
 }
 
 int launch_relax_tail(const RelaxTail& a, cudaStream_t stream) {

@@ -149,7 +149,8 @@ class RelaxationEngine(_EngineBase):
     def __init__(self, cano: torch.Tensor, frames: torch.Tensor, num_parts: int, ctx: Optional[DistContext] = None,
                  trans_lr: float = 1e-2, seg_lr: float = 1e-3, weight_decay: float = 0.0, use_graph: bool = True,
                  seed: int = 2, flow_ref=None, cano_idx: int = 0, lambda_flow: float = 1.0, robust_flow: bool = False,
-                 native: Optional[bool] = None, betas=(0.9, 0.999), eps: float = 1e-8, assign: Optional[dict] = None):
+                 native: Optional[bool] = None, betas=(0.9, 0.999), eps: float = 1e-8, assign: Optional[dict] = None,
+                 cull: Optional[bool] = None):
         """assign: optional dict(downsample=4, assign_gap=5, lambda_assign=0.3, assign_iter=0, mode="add"|"replace")
         enabling the assignment loss (run_robot.py:164-187): from iteration ``assign_iter`` on it is ADDED to the Chamfer
         loss (run_real.py / run_sapien.py) or REPLACES it (run_robot.py's if/else); assignments are refreshed
@@ -170,6 +171,18 @@ class RelaxationEngine(_EngineBase):
         self.total_frames = int(frames.shape[0])
         self.cano = cano.float().contiguous()
         self.frames = frames[lo:hi].float().contiguous()          # local shard of the observed frames
+        # Exact tile culling (csrc/cull.cu): on by default for the native fused iteration.  The loss is invariant to the
+        # order of the points inside a cloud, so both clouds are put into k-d leaf order ONCE here (256-point leaves for
+        # the canonical cloud = one warp of the search, 32-point leaves for the observed frames = one target chunk);
+        # ``perm_cano`` / ``perm_frames`` map engine order -> caller order (engine.skinned[:, k] is caller point perm_cano[k]).
+        self.cull = (flow_ref is None and native is not False) if cull is None else bool(cull)
+        self.perm_cano = self.perm_frames = None
+        cano_orig, frames_orig = self.cano, self.frames
+        if self.cull:
+            self.perm_cano = ops.kd_order(self.cano[None], 256)[0]
+            self.perm_frames = ops.kd_order(self.frames, 32)
+            self.cano = self.cano[self.perm_cano].contiguous()
+            self.frames = torch.gather(self.frames, 1, self.perm_frames[:, :, None].expand(-1, -1, 3)).contiguous()
         self.frames_packed = ops.pack_cloud(self.frames)          # constant over the optimisation: packed once
         torch.manual_seed(seed)                                    # identical init + gumbel draws on every rank
         torch.cuda.manual_seed_all(seed)
@@ -195,6 +208,16 @@ class RelaxationEngine(_EngineBase):
             self.assign_mode = cfg.pop("mode", "add")
             if self.assign_mode not in ("add", "replace"):
                 raise ValueError("assign mode must be 'add' (run_real/run_sapien) or 'replace' (run_robot)")
+            if self.cull:
+                # sample the clouds in the CALLER's order (FPS starts at the caller's point 0, like the reference's
+                # kernel), then express the samples in engine order
+                from .assign import farthest_point_sample
+                n_fps = self.cano.shape[0] // int(cfg.get("downsample", 4))
+                inv_c = torch.empty_like(self.perm_cano); inv_c[self.perm_cano] = torch.arange(len(inv_c), device=dev)
+                inv_f = torch.empty_like(self.perm_frames)
+                inv_f.scatter_(1, self.perm_frames, torch.arange(inv_f.shape[1], device=dev)[None].expand_as(inv_f))
+                cfg["src_idx"] = inv_c[farthest_point_sample(cano_orig[None], n_fps)[0]]
+                cfg["tgt_idx"] = torch.gather(inv_f, 1, farthest_point_sample(frames_orig, n_fps))
             self.assign = AssignLoss(self.cano, self.frames, **cfg)
         self.native = (flow_ref is None) if native is None else bool(native)
         if self.native:
@@ -231,10 +254,14 @@ class RelaxationEngine(_EngineBase):
             shape = (nseg,) if ref is None else tuple(ref.shape)
             b["m_" + k], b["v_" + k] = torch.zeros(shape, **f32), torch.zeros(shape, **f32)
         b["step"] = torch.zeros(1, **f32)
-        b["tickets"] = torch.zeros(2, dtype=torch.int32, device=dev)
+        b["tickets"] = torch.zeros(int(L.reart_relax_tail_ticket_words(N)), dtype=torch.int32, device=dev)
         b["bucket"] = torch.zeros(nseg + 1, **f32)
         b["loss_out"] = torch.zeros(1, **f32)
         b["dims"] = (T, N, M, P, H)
+        if self.cull:                                            # arg-mins carried from step to step (-1: none yet)
+            b["nn_rows"] = torch.full((T, N), -1, dtype=torch.int32, device=dev)
+            b["nn_cols"] = torch.full((T, M), -1, dtype=torch.int32, device=dev)
+            b["cull_stats"] = torch.zeros(2, dtype=torch.int64, device=dev)
         red = self.sink.reducer if self.sink is not None else None
         self.model.seg_head.grad_sink = None                     # the autograd sink is not used on this path
         oneshot = red if (red is not None and hasattr(red, "peer_base")) else None
@@ -271,7 +298,10 @@ class RelaxationEngine(_EngineBase):
         return super()._opt_state_tensors()
 
     def _aux_state_tensors(self):
-        return [self.assign.col4row, self.assign.dual_u] if self.assign is not None else []
+        aux = [self.assign.col4row, self.assign.dual_u] if self.assign is not None else []
+        if self.native and self.cull:
+            aux += [self._nat["nn_rows"], self._nat["nn_cols"], self._nat["cull_stats"]]
+        return aux
 
     # ------------------------------------------------------------------------------------------ iteration flavours
     def _phase(self):
@@ -293,6 +323,31 @@ class RelaxationEngine(_EngineBase):
     def _step_phase(self):
         return getattr(self, "_cur_variant", None) or self._phase()
 
+    def _energy_call(self, L, b, T, N, M, P, gW, gR, gtr, g_skinned, compute_grad):
+        """The fused energy evaluation of this step: brute-force search, or the exact culled one seeded by the previous
+        step's arg-mins (bit-identical results)."""
+        from ._lib import check, ptr, stream_ptr
+        m = self.model
+        if self.cull:
+            check(L.reart_skinned_chamfer_fwd_bwd_culled(
+                ptr(self.cano), ptr(b["W"]), ptr(b["R"]), ptr(m.proposal_t), ptr(self.frames), ptr(self.frames_packed), T, N, M, P,
+                ptr(b["skinned"]), ptr(b["loss64"]), ptr(gW), ptr(gR), ptr(gtr), ptr(g_skinned), compute_grad, None, None, None,
+                None, ptr(b["nn_rows"]), ptr(b["nn_cols"]), ptr(b["cull_stats"]), ptr(b["ws"]), b["ws_bytes"], stream_ptr()),
+                "reart_skinned_chamfer_fwd_bwd_culled")
+        else:
+            check(L.reart_skinned_chamfer_fwd_bwd(
+                ptr(self.cano), ptr(b["W"]), ptr(b["R"]), ptr(m.proposal_t), ptr(self.frames), ptr(self.frames_packed), T, N, M, P,
+                ptr(b["skinned"]), ptr(b["loss64"]), ptr(gW), ptr(gR), ptr(gtr), ptr(g_skinned), compute_grad, ptr(b["ws"]),
+                b["ws_bytes"], stream_ptr()), "reart_skinned_chamfer_fwd_bwd")
+
+    def culling_stats(self):
+        """(evaluated, offered) (warp, 32-target chunk) pairs since the last call; resets the counters.  Host sync."""
+        if not (self.native and self.cull):
+            return None
+        ev, off = (int(x) for x in self._nat["cull_stats"].tolist())
+        self._nat["cull_stats"].zero_()
+        return ev, off
+
     def _run_iteration_native(self):
         """head -> [memset, skin (x-sorted copy), search, energy columns, energy rows, skin backward, reduce] -> tail."""
         import ctypes
@@ -307,23 +362,17 @@ class RelaxationEngine(_EngineBase):
         b["expo"].exponential_()                                  # the same RNG draw F.gumbel_softmax makes
         with torch.cuda.device(self.cano.device):
             check(L.reart_relax_head(ptr(self.cano), ptr(conv0.weight), ptr(conv0.bias), ptr(conv2.weight), ptr(b["expo"]),
-                                     ptr(self.tau), ptr(m.proposal_6d), N, H, P, T, None, ptr(b["W"]), ptr(b["ysoft"]),
+                                     ptr(self.perm_cano), ptr(self.tau), ptr(m.proposal_6d), N, H, P, T, None, ptr(b["W"]), ptr(b["ysoft"]),
                                      ptr(b["R"]), stream_ptr()), "reart_relax_head")
             if not use_assign:
-                check(L.reart_skinned_chamfer_fwd_bwd(ptr(self.cano), ptr(b["W"]), ptr(b["R"]), ptr(m.proposal_t), ptr(self.frames),
-                                                      ptr(self.frames_packed), T, N, M, P, ptr(b["skinned"]), ptr(b["loss64"]),
-                                                      ptr(b["gW"]), ptr(b["gR"]), ptr(b["gtr"]), None, 1, ptr(b["ws"]),
-                                                      b["ws_bytes"], stream_ptr()), "reart_skinned_chamfer_fwd_bwd")
+                self._energy_call(L, b, T, N, M, P, b["gW"], b["gR"], b["gtr"], None, 1)
             else:
                 if "gs" not in b:
                     b["gs"] = torch.zeros(T, N, 3, dtype=torch.float32, device=self.cano.device)
                     b["bwd_ws_bytes"] = int(L.reart_skin_bwd_workspace_bytes(T, N, P))
                     b["bwd_ws"] = _lib.workspace(b["bwd_ws_bytes"], self.cano.device)
                 if use_chamfer:                                   # Chamfer energy and its gradient w.r.t. the skinned cloud
-                    check(L.reart_skinned_chamfer_fwd_bwd(ptr(self.cano), ptr(b["W"]), ptr(b["R"]), ptr(m.proposal_t),
-                                                          ptr(self.frames), ptr(self.frames_packed), T, N, M, P, ptr(b["skinned"]),
-                                                          ptr(b["loss64"]), None, None, None, ptr(b["gs"]), 0, ptr(b["ws"]),
-                                                          b["ws_bytes"], stream_ptr()), "reart_skinned_chamfer_fwd_bwd")
+                    self._energy_call(L, b, T, N, M, P, None, None, None, b["gs"], 0)
                 else:                                             # run_robot.py:164-192: the assignment loss REPLACES Chamfer
                     check(L.reart_skin_fwd(ptr(self.cano), ptr(b["W"]), ptr(b["R"]), ptr(m.proposal_t), T, N, P, ptr(b["skinned"]),
                                            stream_ptr()), "reart_skin_fwd")

@@ -434,6 +434,35 @@ def skinned_chamfer_loss(cano, W, R, tr, tgt, tgt_packed=None, unit_grad: bool =
     return _SkinnedChamfer.apply(cano, W, R, tr, tgt, tgt_packed, unit_grad)
 
 
+# --------------------------------------------------------------------------------------- k-d leaf ordering (culling)
+@torch.no_grad()
+def kd_order(points: torch.Tensor, leaf: int) -> torch.Tensor:
+    """Permutation [B,N] that orders every cloud of ``points`` [B,N,3] into k-d leaves of ``leaf`` consecutive points
+    (recursive median split along the longest axis of each segment), so that consecutive index ranges are spatially
+    compact.  Pure torch, one batched sort per level; meant to run ONCE per cloud at set-up.  The exact culled search
+    (``reart_skinned_chamfer_fwd_bwd_culled``) is correct for any order and fast for this one."""
+    B, N, _ = points.shape
+    levels = 0
+    while (leaf << levels) < N:
+        levels += 1
+    n_pad = leaf << levels
+    pts = points.float()
+    if n_pad != N:                                             # far-away padding: sorts last, is dropped at the end
+        pts = torch.cat((pts, torch.full((B, n_pad - N, 3), 1e30, dtype=pts.dtype, device=pts.device)), dim=1)
+    idx = torch.arange(n_pad, device=pts.device)[None].expand(B, n_pad).contiguous()
+    for level in range(levels):
+        segs, seg = 1 << level, n_pad >> level
+        P = torch.gather(pts, 1, idx[:, :, None].expand(-1, -1, 3)).view(B, segs, seg, 3)
+        axis = (P.amax(dim=2) - P.amin(dim=2)).argmax(dim=-1)                                  # [B, segs]
+        key = torch.gather(P, 3, axis[:, :, None, None].expand(-1, -1, seg, 1))[..., 0]         # [B, segs, seg]
+        order = key.argsort(dim=-1, stable=True)
+        idx = torch.gather(idx.view(B, segs, seg), 2, order).view(B, n_pad)
+    if n_pad != N:
+        keep = idx < N
+        idx = idx[keep].view(B, N)
+    return idx
+
+
 def fp32_probe(variant: int, iters: int = 2000, blocks: int | None = None, device=None):
     """Run one FP32 pipe micro-benchmark; returns (ms, lane_ops_total)."""
     L = _lib.lib()

@@ -608,7 +608,7 @@ def test_relax_head_equals_the_separate_kernels():
     d6 = torch.randn(T, P, 6, device=dev(), generator=g)
     logits, W, ys = (torch.empty(N, P, device=dev()) for _ in range(3))
     R = torch.empty(T, P, 3, 3, device=dev())
-    _lib.check(L.reart_relax_head(_lib.ptr(x), _lib.ptr(w0), _lib.ptr(b0), _lib.ptr(w2), _lib.ptr(expo), _lib.ptr(tau), _lib.ptr(d6),
+    _lib.check(L.reart_relax_head(_lib.ptr(x), _lib.ptr(w0), _lib.ptr(b0), _lib.ptr(w2), _lib.ptr(expo), None, _lib.ptr(tau), _lib.ptr(d6),
                                   N, H, P, T, _lib.ptr(logits), _lib.ptr(W), _lib.ptr(ys), _lib.ptr(R), _lib.stream_ptr()), "head")
     lg2 = ops.seg_mlp(x, w0, b0, w2)
     W2, ys2 = torch.empty_like(W), torch.empty_like(ys)

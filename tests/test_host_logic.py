@@ -86,9 +86,10 @@ def test_built_library_is_sm100a_sass_with_bulk_tma_and_packed_fp32():
     arch, kernels = sass_summary.census()
     assert arch == ["sm_100a"]
     by = lambda frag: [k for n, k in kernels.items() if frag in n]
-    sym = by("chamfer_sym_kernelILi8ELi1E")
-    assert len(sym) == 1 and sym[0]["UBLKCP"] >= 2 and sym[0]["FFMA2"] > 100 and sym[0]["FADD2"] > 100 and sym[0]["FMNMX3"] > 50
-    assert sym[0]["REDUX"] > 10
+    sym = by("chamfer_sym_kernelILi8ELi1E")                   # brute-force and culled instantiation
+    assert len(sym) == 2
+    for k in sym:
+        assert k["UBLKCP"] >= 2 and k["FFMA2"] > 100 and k["FADD2"] > 100 and k["FMNMX3"] > 50 and k["REDUX"] > 10
     assert all(k["UBLKCP"] >= 1 and k["FFMA2"] > 0 for k in by("knn1_main_kernel"))
     assert sum(k["UTCMMA|HGMMA|HMMA"] for k in kernels.values()) == 0
     for frag in ("skin_bwd_fused_kernel", "skin_bwd_reduce_kernel", "energy_rows_kernel", "skin_fwd_sorted_kernel",
