@@ -283,7 +283,7 @@ def kernels_of_one_step(engine):
         return None, {}
 
 
-def make_engine(workload, ctx, dev, use_graph, scaling, extra_losses=True):
+def make_engine(workload, ctx, dev, use_graph, scaling, extra_losses=True, cull=False):
     """Synthetic sequence + engine of one named workload.  Returns (engine, host cano, host frames, T_total, N, P, desc)."""
     import numpy as np
     import torch
@@ -316,7 +316,7 @@ def make_engine(workload, ctx, dev, use_graph, scaling, extra_losses=True):
         engine = RelaxationEngine(cano_h.to(dev), frames_h.to(dev), num_parts=P, ctx=ctx, use_graph=use_graph, flow_ref=fr,
                                   cano_idx=0, **kwargs)
     else:
-        engine = RelaxationEngine(cano_h.to(dev), frames_h.to(dev), num_parts=P, ctx=ctx, use_graph=use_graph)
+        engine = RelaxationEngine(cano_h.to(dev), frames_h.to(dev), num_parts=P, ctx=ctx, use_graph=use_graph, cull=cull)
     return engine, cano_h, frames_h, T_total, N, P, desc
 
 
@@ -420,6 +420,31 @@ def sustained_run(engine, ctx, seconds, ms_per_step_hint, gpu_index, uuid, pairs
     return out
 
 
+def culled_entry(workload, ctx, dev, flush, steps, warmup, scaling, brute_loss, brute_ms):
+    """The workload on RelaxationEngine(cull=True): k-d leaf order at set-up, bounds seeded by the previous step's arg-mins,
+    bit-identical search results (tests/test_cull_gpu.py); reports ms/step and the fraction of blocks evaluated."""
+    import torch
+    engine, _, _, T_total, N, P, _ = make_engine(workload, ctx, dev, True, scaling, extra_losses=False, cull=True)
+    ms, _, loss = time_engine_steps(engine, ctx, steps, warmup, flush)
+    final = float(loss.item())
+    engine.culling_stats()
+    for _ in range(5):
+        engine.step()
+    st = engine.culling_stats()
+    engine.release()
+    del engine
+    torch.cuda.empty_cache()
+    pairs = 2.0 * T_total * N * N
+    return {"enabled_in_headline": False, "ms_per_step": ms, "value": pairs / (ms * 1e-3), "unit": UNIT,
+            "speedup_vs_brute_force_step": brute_ms / ms, "final_loss": final, "final_loss_brute_force": brute_loss,
+            "block_pairs_evaluated": st[0] if st else None, "block_pairs_offered": st[1] if st else None,
+            "fraction_evaluated": (st[0] / st[1]) if st and st[1] else None,
+            "what": "opt-in exact tile culling (csrc/cull.cu, RelaxationEngine(cull=True)): (256-row, 32-target) blocks whose "
+                    "bounding-box gap exceeds the upper bounds seeded by the previous step's arg-mins are skipped; search keys "
+                    "bit-identical to the brute force on the same clouds (tests/test_cull_gpu.py); the engine reorders both "
+                    "clouds into k-d leaves, so float sums associate differently and the losses agree to rounding, not bits"}
+
+
 def sweep_entry(workload, ctx, dev, flush, steps, warmup, peak_tf):
     import torch
     engine, _, _, T_total, N, P, desc = make_engine(workload, ctx, dev, True, "strong")
@@ -437,6 +462,12 @@ def sweep_entry(workload, ctx, dev, flush, steps, warmup, peak_tf):
     engine.release()
     del engine
     torch.cuda.empty_cache()
+    if workload not in ("cfg4", "cfg2"):
+        try:
+            c = culled_entry(workload, ctx, dev, flush, steps, warmup, "strong", final_loss, ms)
+            ent["culled"] = {k: c[k] for k in ("ms_per_step", "value", "speedup_vs_brute_force_step", "fraction_evaluated", "final_loss")}
+        except Exception as exc:
+            ent["culled"] = {"error": f"{type(exc).__name__}: {exc}"}
     return ent
 
 
@@ -552,19 +583,6 @@ def main():
     e2e_value = pairs_per_step / (float(t2.item()) * 1e-3)
     _ = float(host_loss)
 
-    culling = None
-    if getattr(engine, "cull", False) and hasattr(engine, "culling_stats"):
-        engine.culling_stats()                                    # reset, then measure over a few steady-state steps
-        for _ in range(5):
-            engine.step()
-        st = engine.culling_stats()
-        if st and st[1]:
-            culling = {"enabled": True, "block_pairs_evaluated": st[0], "block_pairs_offered": st[1],
-                       "fraction_evaluated": st[0] / st[1],
-                       "what": "exact tile culling (csrc/cull.cu): (256-row, 32-target) blocks whose bounding-box gap exceeds the "
-                               "upper bounds seeded by the previous step's arg-mins are skipped; results bit-identical to the "
-                               "brute-force search, which stays the kernel the roofline is quoted on"}
-
     # ---- roofline of the dominant kernel (chamfer_sym_kernel), timed alone with CUDA events on this stream
     Tl = hi - lo
     k_ms, local_pairs, alg_bytes = search_kernel_timing(engine, flush)
@@ -605,11 +623,20 @@ def main():
         sustained = sustained_run(engine, ctx, args.sustained_s, ms_per_step, ctx.local_rank, uuid, pairs_per_step,
                                   k_ms / ms_per_step, peak_tf, sm_max_mhz)
 
-    # ---- sweep over the other BASELINE configs (N=1) / candidate fits (N>1)
-    sweep = None
     engine.release()
     del engine
     torch.cuda.empty_cache()
+
+    # ---- the same workload with the opt-in exact tile culling (a second engine; the headline above is the brute force)
+    culling = None
+    if args.workload != "cfg4":
+        try:
+            culling = culled_entry(args.workload, ctx, dev, flush, K, W, args.scaling, final_loss, ms_per_step)
+        except Exception as exc:
+            culling = {"error": f"{type(exc).__name__}: {exc}"}
+
+    # ---- sweep over the other BASELINE configs (N=1) / candidate fits (N>1)
+    sweep = None
     if not args.no_sweep and args.workload == "cfg3_16k":
         sweep = []
         if world == 1:

@@ -13,6 +13,11 @@ constexpr int64_t kAlign = 256;
 inline int64_t align_up(int64_t v) { return round_up(v, kAlign); }
 inline bool fits_int(int64_t v) { return v >= 0 && v <= 0x7fffffff; }
 
+// The launch checks below read cudaGetLastError(): a NON-sticky error left behind by some other library on this thread
+// (seen in practice after a CUPTI profiling session) must not be reported as ours, so every entry point starts by clearing it.
+// A sticky error (a real fault) survives the clear and is still reported.
+#define REART_ENTRY() (void)cudaGetLastError()
+
 struct Carver {
     char* base;
     int64_t off;
@@ -57,6 +62,7 @@ int64_t reart_knn1_workspace_bytes(int64_t B, int64_t P1, int64_t P2) {
 
 int reart_knn1_fwd(const float* p1, const float* p2, int64_t B, int64_t P1, int64_t P2, float* dists, int64_t* idx,
                    void* workspace, int64_t workspace_bytes, void* stream_) {
+    REART_ENTRY();
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (B < 0 || P1 < 0 || P2 < 0 || !fits_int(B) || !fits_int(P1) || !fits_int(padded_points(P2)))
         return REART_ERR_INVALID_ARG;
@@ -92,6 +98,7 @@ int64_t reart_chamfer_workspace_bytes(int64_t B, int64_t N, int64_t M) {
 int reart_chamfer_bidir_fwd(const float* src, const float* tgt, int64_t B, int64_t N, int64_t M, float* d_fwd,
                             int64_t* i_fwd, float* d_bwd, int64_t* i_bwd, void* workspace, int64_t workspace_bytes,
                             void* stream_) {
+    REART_ENTRY();
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (B < 0 || N < 0 || M < 0 || !fits_int(B) || !fits_int(padded_points(N)) || !fits_int(padded_points(M)))
         return REART_ERR_INVALID_ARG;
@@ -134,6 +141,7 @@ int reart_chamfer_bidir_fwd(const float* src, const float* tgt, int64_t B, int64
 
 int reart_chamfer_sym_search(const float* src, const float* tgt_packed, int64_t B, int64_t N, int64_t M,
                              uint64_t* keys_a, uint64_t* keys_b, int32_t* col_chunk_pts, int variant, void* stream_) {
+    REART_ENTRY();
     if (B <= 0 || N <= 0 || M <= 0 || !fits_int(B) || !fits_int(padded_points(N)) || !fits_int(padded_points(M)))
         return REART_ERR_INVALID_ARG;
     if (!src || !tgt_packed || !keys_a || !keys_b) return REART_ERR_INVALID_ARG;
@@ -149,6 +157,7 @@ int reart_chamfer_sym_search(const float* src, const float* tgt_packed, int64_t 
 
 int reart_knn1_bwd(const float* p1, const float* p2, const int64_t* idx, const float* grad_dists, int64_t B,
                    int64_t P1, int64_t P2, float* grad_p1, float* grad_p2, void* stream_) {
+    REART_ENTRY();
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (B < 0 || P1 < 0 || P2 < 0) return REART_ERR_INVALID_ARG;
     if (B == 0) return REART_OK;
@@ -159,6 +168,7 @@ int reart_knn1_bwd(const float* p1, const float* p2, const int64_t* idx, const f
 int reart_chamfer_bidir_bwd(const float* src, const float* tgt, const int64_t* i_fwd, const int64_t* i_bwd,
                             const float* g_fwd, const float* g_bwd, int64_t B, int64_t N, int64_t M, float* grad_src,
                             float* grad_tgt, void* stream_) {
+    REART_ENTRY();
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (B < 0 || N < 0 || M < 0) return REART_ERR_INVALID_ARG;
     if (B == 0) return REART_OK;
@@ -172,6 +182,7 @@ int64_t reart_packed_bytes(int64_t B, int64_t P) {
 }
 
 int reart_pack_cloud(const float* pts, int64_t B, int64_t P, float* packed, void* stream_) {
+    REART_ENTRY();
     if (B < 0 || P < 0 || !fits_int(padded_points(P))) return REART_ERR_INVALID_ARG;
     if (B == 0) return REART_OK;
     if (!packed || (P > 0 && !pts)) return REART_ERR_INVALID_ARG;
@@ -180,6 +191,7 @@ int reart_pack_cloud(const float* pts, int64_t B, int64_t P, float* packed, void
 
 int reart_skin_fwd(const float* cano, const float* W, const float* R, const float* tr, int64_t T, int64_t N, int64_t P,
                    float* out, void* stream_) {
+    REART_ENTRY();
     if (T < 0 || N < 0 || P < 0 || !fits_int(T) || !fits_int(N)) return REART_ERR_INVALID_ARG;
     if (T == 0 || N == 0) return REART_OK;
     if (!cano || !W || !R || !tr || !out) return REART_ERR_INVALID_ARG;
@@ -194,6 +206,7 @@ int64_t reart_skin_bwd_workspace_bytes(int64_t T, int64_t N, int64_t P) {
 int reart_skin_bwd(const float* cano, const float* W, const float* R, const float* tr, const float* g, int64_t T,
                    int64_t N, int64_t P, float* gW, float* gR, float* gtr, void* workspace, int64_t workspace_bytes,
                    void* stream_) {
+    REART_ENTRY();
     if (T < 0 || N < 0 || P < 0 || !fits_int(T) || !fits_int(N)) return REART_ERR_INVALID_ARG;
     if ((N * P > 0 && !gW) || (T * P > 0 && (!gR || !gtr))) return REART_ERR_INVALID_ARG;
     if (T > 0 && N > 0 && (!cano || !W || !R || !tr || !g)) return REART_ERR_INVALID_ARG;
@@ -216,6 +229,7 @@ int reart_skinned_chamfer_fwd_bwd(const float* cano, const float* W, const float
                                   const float* tgt_packed, int64_t T, int64_t N, int64_t M, int64_t P, float* skinned,
                                   double* loss, float* gW, float* gR, float* gtr, float* g_skinned, int compute_grad,
                                   void* workspace, int64_t workspace_bytes, void* stream_) {
+    REART_ENTRY();
     return reart_skinned_chamfer_fwd_bwd_ex(cano, W, R, tr, tgt, tgt_packed, T, N, M, P, skinned, loss, gW, gR, gtr, g_skinned,
                                             compute_grad, nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes, stream_);
 }
@@ -225,6 +239,7 @@ int reart_skinned_chamfer_fwd_bwd_ex(const float* cano, const float* W, const fl
                                      double* loss, float* gW, float* gR, float* gtr, float* g_skinned, int compute_grad,
                                      float* d_fwd, int64_t* i_fwd, float* d_bwd, int64_t* i_bwd, void* workspace,
                                      int64_t workspace_bytes, void* stream_) {
+    REART_ENTRY();
     return reart_skinned_chamfer_fwd_bwd_culled(cano, W, R, tr, tgt, tgt_packed, T, N, M, P, skinned, loss, gW, gR, gtr, g_skinned,
                                                 compute_grad, d_fwd, i_fwd, d_bwd, i_bwd, nullptr, nullptr, nullptr, workspace,
                                                 workspace_bytes, stream_);
@@ -236,6 +251,7 @@ int reart_skinned_chamfer_fwd_bwd_culled(const float* cano, const float* W, cons
                                          float* g_skinned, int compute_grad, float* d_fwd, int64_t* i_fwd, float* d_bwd,
                                          int64_t* i_bwd, int32_t* nn_rows, int32_t* nn_cols, uint64_t* cull_stats,
                                          void* workspace, int64_t workspace_bytes, void* stream_) {
+    REART_ENTRY();
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (T <= 0 || N <= 0 || M <= 0 || P <= 0 || P > 32 || !fits_int(T) || !fits_int(padded_points(N)) ||
         !fits_int(padded_points(M)))
@@ -298,6 +314,7 @@ int reart_skinned_chamfer_fwd_bwd_culled(const float* cano, const float* W, cons
 
 int reart_segmlp_fwd(const float* x, const float* w0, const float* b0, const float* w2, int64_t N, int64_t H, int64_t P,
                      float* logits, void* stream_) {
+    REART_ENTRY();
     if (N < 0 || H <= 0 || P <= 0) return REART_ERR_INVALID_ARG;
     if (N == 0) return REART_OK;
     if (!x || !w0 || !b0 || !w2 || !logits) return REART_ERR_INVALID_ARG;
@@ -307,6 +324,7 @@ int reart_segmlp_fwd(const float* x, const float* w0, const float* b0, const flo
 
 int reart_segmlp_bwd(const float* x, const float* w0, const float* b0, const float* w2, const float* glogits, int64_t N,
                      int64_t H, int64_t P, float* gw0, float* gb0, float* gw2, void* stream_) {
+    REART_ENTRY();
     if (N < 0 || H <= 0 || P <= 0 || !gw0 || !gb0 || !gw2) return REART_ERR_INVALID_ARG;
     if (N > 0 && (!x || !w0 || !b0 || !w2 || !glogits)) return REART_ERR_INVALID_ARG;
     if (N == 0) {
@@ -321,6 +339,7 @@ int reart_segmlp_bwd(const float* x, const float* w0, const float* b0, const flo
 
 int reart_gumbel_st_fwd(const float* logits, const float* expo, const float* tau, int64_t N, int64_t P, float* W,
                         float* ysoft, void* stream_) {
+    REART_ENTRY();
     if (N < 0 || P <= 0) return REART_ERR_INVALID_ARG;
     if (N == 0) return REART_OK;
     if (!logits || !expo || !tau || !W || !ysoft) return REART_ERR_INVALID_ARG;
@@ -329,6 +348,7 @@ int reart_gumbel_st_fwd(const float* logits, const float* expo, const float* tau
 
 int reart_gumbel_st_bwd(const float* ysoft, const float* tau, const float* gW, int64_t N, int64_t P, float* glogits,
                         void* stream_) {
+    REART_ENTRY();
     if (N < 0 || P <= 0) return REART_ERR_INVALID_ARG;
     if (N == 0) return REART_OK;
     if (!ysoft || !tau || !gW || !glogits) return REART_ERR_INVALID_ARG;
@@ -339,6 +359,7 @@ int reart_gumbel_st_bwd(const float* ysoft, const float* tau, const float* gW, i
 int reart_relax_head(const float* cano, const float* w0, const float* b0, const float* w2, const float* expo,
                      const int64_t* noise_index, const float* tau, const float* d6, int64_t N, int64_t H, int64_t P, int64_t T, float* logits,
                      float* W, float* ysoft, float* R, void* stream_) {
+    REART_ENTRY();
     if (N < 0 || T < 0 || H <= 0 || P <= 0 || !fits_int(4 * N) || !fits_int(T * P)) return REART_ERR_INVALID_ARG;
     if (N > 0 && (!cano || !w0 || !b0 || !w2 || !expo || !tau || !W || !ysoft)) return REART_ERR_INVALID_ARG;
     if (T > 0 && (!d6 || !R)) return REART_ERR_INVALID_ARG;
@@ -354,6 +375,7 @@ int64_t reart_relax_tail_workspace_bytes(int64_t N, int64_t H, int64_t P) {
 int64_t reart_relax_tail_ticket_words(int64_t N) { return N < 0 ? -1 : relax_tail_ticket_words(N); }
 
 int reart_relax_tail(const reart_relax_tail_args* x, void* stream_) {
+    REART_ENTRY();
     if (!x || x->N <= 0 || x->T <= 0 || x->H <= 0 || x->P <= 0 || !fits_int(x->N) || !fits_int(x->T * x->P))
         return REART_ERR_INVALID_ARG;
     if (!x->cano || !x->w0 || !x->b0 || !x->w2 || !x->ysoft || !x->tau || !x->gW || !x->d6 || !x->tr || !x->gR || !x->gtr ||
@@ -375,6 +397,7 @@ int reart_relax_tail(const reart_relax_tail_args* x, void* stream_) {
 }
 
 int reart_rot6d_fwd(const float* d6, int64_t B, float* R, void* stream_) {
+    REART_ENTRY();
     if (B < 0) return REART_ERR_INVALID_ARG;
     if (B == 0) return REART_OK;
     if (!d6 || !R) return REART_ERR_INVALID_ARG;
@@ -382,6 +405,7 @@ int reart_rot6d_fwd(const float* d6, int64_t B, float* R, void* stream_) {
 }
 
 int reart_rot6d_bwd(const float* d6, const float* gR, int64_t B, float* gd6, void* stream_) {
+    REART_ENTRY();
     if (B < 0) return REART_ERR_INVALID_ARG;
     if (B == 0) return REART_OK;
     if (!d6 || !gR || !gd6) return REART_ERR_INVALID_ARG;
@@ -390,6 +414,7 @@ int reart_rot6d_bwd(const float* d6, const float* gR, int64_t B, float* gd6, voi
 
 int reart_screw_to_transform_fwd(const float* l, const float* m, const float* theta, const float* d, int64_t B,
                                  float* M, void* stream_) {
+    REART_ENTRY();
     if (B < 0) return REART_ERR_INVALID_ARG;
     if (B == 0) return REART_OK;
     if (!l || !m || !theta || !d || !M) return REART_ERR_INVALID_ARG;
@@ -398,6 +423,7 @@ int reart_screw_to_transform_fwd(const float* l, const float* m, const float* th
 
 int reart_screw_to_transform_bwd(const float* l, const float* m, const float* theta, const float* d, const float* gM,
                                  int64_t B, float* gl, float* gm, float* gtheta, float* gd, void* stream_) {
+    REART_ENTRY();
     if (B < 0) return REART_ERR_INVALID_ARG;
     if (B == 0) return REART_OK;
     if (!l || !m || !theta || !d || !gM || !gl || !gm || !gtheta || !gd) return REART_ERR_INVALID_ARG;
@@ -407,6 +433,7 @@ int reart_screw_to_transform_bwd(const float* l, const float* m, const float* th
 int reart_fk_fwd(const float* axis, const float* moment, const float* theta, const float* distance,
                  const int32_t* order, const int32_t* parent, const int32_t* edge, const int32_t* joint_type, int64_t T,
                  int64_t P, float* out, void* stream_) {
+    REART_ENTRY();
     if (T < 0 || P < 0 || !fits_int(T) || !fits_int(P)) return REART_ERR_INVALID_ARG;
     if (T == 0 || P == 0) return REART_OK;
     if (!order || !parent || !edge || !out || (P > 1 && (!axis || !moment || !theta))) return REART_ERR_INVALID_ARG;
@@ -418,6 +445,7 @@ int reart_fk_bwd(const float* axis, const float* moment, const float* theta, con
                  const int32_t* order, const int32_t* parent, const int32_t* edge, const int32_t* joint_type, int64_t T,
                  int64_t P, const float* fk_out, const float* g_out, float* g_axis, float* g_moment, float* g_theta,
                  float* g_dist, float* workspace, void* stream_) {
+    REART_ENTRY();
     if (T < 0 || P < 0 || !fits_int(T) || !fits_int(P)) return REART_ERR_INVALID_ARG;
     if (T == 0 || P <= 1) return REART_OK;
     if (!order || !parent || !edge || !fk_out || !g_out || !axis || !moment || !theta || !g_axis || !g_moment ||
@@ -430,6 +458,7 @@ int reart_fk_bwd(const float* axis, const float* moment, const float* theta, con
 
 int reart_knn(const float* ref, const float* query, int64_t B, int64_t n, int64_t m, int k, float* dist, int64_t* idx,
               void* stream_) {
+    REART_ENTRY();
     if (B < 0 || n < 0 || m < 0 || k < 1 || k > 8 || !fits_int(n) || !fits_int(m)) return REART_ERR_INVALID_ARG;
     if (B == 0 || m == 0) return REART_OK;
     if (n < k) return REART_ERR_INVALID_ARG;
@@ -439,6 +468,7 @@ int reart_knn(const float* ref, const float* query, int64_t B, int64_t n, int64_
 
 int reart_knn3_blend(const float* query, const float* ref_cat, const float* flow_cat, const int64_t* ref_offsets,
                      int64_t T, int64_t m, float* blended, uint8_t* mask, void* stream_) {
+    REART_ENTRY();
     if (T < 0 || m < 0 || !fits_int(m)) return REART_ERR_INVALID_ARG;
     if (T == 0 || m == 0) return REART_OK;
     if (!query || !ref_cat || !flow_cat || !ref_offsets || !blended) return REART_ERR_INVALID_ARG;
@@ -448,6 +478,7 @@ int reart_knn3_blend(const float* query, const float* ref_cat, const float* flow
 
 int reart_lap(const float* src, const int64_t* src_idx, int64_t src_points, const float* tgt, int64_t B, int64_t n,
               int32_t* col4row, double* total, double* dual_u, int warm_start, void* stream_) {
+    REART_ENTRY();
     if (B < 0 || n < 0 || src_points < 0) return REART_ERR_INVALID_ARG;
     if (B == 0 || n == 0) return REART_OK;
     if (!src || !tgt || !col4row || (!src_idx && src_points < n)) return REART_ERR_INVALID_ARG;
@@ -459,6 +490,7 @@ int reart_lap(const float* src, const int64_t* src_idx, int64_t src_points, cons
 int reart_assign_loss_grad(const float* skinned, const int64_t* src_idx, const float* tgt, const int32_t* col4row, int64_t T,
                            int64_t N, int64_t n, float lambda, float* g_skinned, int accumulate, double* loss,
                            void* stream_) {
+    REART_ENTRY();
     if (T < 0 || N < 0 || n < 0) return REART_ERR_INVALID_ARG;
     if (T == 0 || n == 0) return REART_OK;
     if (!skinned || !src_idx || !tgt || !col4row || !loss) return REART_ERR_INVALID_ARG;
@@ -467,6 +499,7 @@ int reart_assign_loss_grad(const float* skinned, const int64_t* src_idx, const f
 }
 
 int reart_fps(const float* xyz, int64_t B, int64_t N, int64_t npoint, int32_t* out, void* stream_) {
+    REART_ENTRY();
     if (B < 0 || N < 0 || npoint < 0) return REART_ERR_INVALID_ARG;
     if (B == 0 || npoint == 0) return REART_OK;
     if (!xyz || !out || N == 0) return REART_ERR_INVALID_ARG;
@@ -475,6 +508,7 @@ int reart_fps(const float* xyz, int64_t B, int64_t N, int64_t npoint, int32_t* o
 
 int reart_ball_query(const float* new_xyz, const float* xyz, int64_t B, int64_t N, int64_t m, float radius,
                      int nsample, int32_t* idx, void* stream_) {
+    REART_ENTRY();
     if (B < 0 || N < 0 || m < 0 || nsample < 0 || !fits_int(N) || !fits_int(m)) return REART_ERR_INVALID_ARG;
     if (B == 0 || m == 0 || nsample == 0) return REART_OK;
     if (!new_xyz || !idx || (N > 0 && !xyz)) return REART_ERR_INVALID_ARG;
@@ -483,6 +517,7 @@ int reart_ball_query(const float* new_xyz, const float* xyz, int64_t B, int64_t 
 
 int reart_allreduce_oneshot(const uint64_t* peer_base, int rank, int world, int64_t n, int64_t n_pad, uint32_t* epoch,
                             float* data, void* stream_) {
+    REART_ENTRY();
     if (world < 1 || rank < 0 || rank >= world || n < 0 || n_pad < n) return REART_ERR_INVALID_ARG;
     if (n == 0 || world == 1) return REART_OK;
     if (!peer_base || !epoch || !data) return REART_ERR_INVALID_ARG;
@@ -492,6 +527,7 @@ int reart_allreduce_oneshot(const uint64_t* peer_base, int rank, int world, int6
 
 int reart_fp32_probe(int variant, int iters, int blocks, const float* scratch_in, float* scratch_out, double* ms,
                      double* ops_per_thread, void* stream_) {
+    REART_ENTRY();
     return launch_probe(variant, iters, blocks, scratch_in, scratch_out, ms, ops_per_thread,
                         static_cast<cudaStream_t>(stream_));
 }

@@ -72,6 +72,39 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymPa
     const int qbase = qb * QB;
     const float* __restrict__ q = p.a + (int64_t)b * p.na * 3;
 
+    const int chunks_total = p.nb_pad / kChunk;
+    const int cps = (chunks_total + p.splits - 1) / p.splits;
+    const int chunk0 = split * cps;
+    const int nchunks = min(cps, chunks_total - chunk0);
+    const int ntiles = (nchunks + C::kTileChunks - 1) / C::kTileChunks;
+    const float* __restrict__ tp = p.b_packed + (int64_t)b * p.nb_pad * 3 + (int64_t)chunk0 * kChunk * 3;
+    u64* __restrict__ keys_col = p.keys_b + (int64_t)b * p.nb;
+    const unsigned colchunk_base = (unsigned)(qbase / C::kColChunkPts);
+
+    unsigned cmax = 0u;                                      // largest finite column minimum this thread merged
+
+    const float* __restrict__ bp = CULL ? p.colbox + ((int64_t)b * chunks_total + chunk0) * kBoxFloats : nullptr;
+    auto issue = [&](int k) {
+        const int st = k % kSymStages;
+        const int nch = min(C::kTileChunks, nchunks - k * C::kTileChunks);
+        const uint32_t bytes = (uint32_t)nch * kChunk * 12;
+        const uint32_t box_bytes = CULL ? (uint32_t)nch * kBoxFloats * 4 : 0u;
+        mbar_expect_tx(&full_bar[st], bytes + box_bytes);
+        tma_bulk_g2s(smem_raw + st * C::kTileBytes, tp + (int64_t)k * C::kTilePoints * 3, bytes, &full_bar[st]);
+        if (CULL)
+            tma_bulk_g2s(sbox + st * C::kTileChunks * kBoxFloats, bp + (int64_t)k * C::kTileChunks * kBoxFloats, box_bytes,
+                         &full_bar[st]);
+    };
+    // the first tiles are requested BEFORE the rows are loaded: the TMA latency of a work item hides behind its own
+    // prologue (small shards under strong scaling run items of a single tile, where it was fully exposed)
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kSymStages; ++s) mbar_init(&full_bar[s], 1);
+        mbar_fence_init();
+        for (int k = 0; k < min(kSymStages, ntiles); ++k) issue(k);
+    }
+
+
     // register r = s*RS + rr holds A point  qbase + warp*32R + s*(32 RS) + lane*RS + rr
     u64 QX[R], QY[R], QZ[R];
     float best[R], prev[R];
@@ -104,39 +137,7 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymPa
         if (rc * (32 * R) < p.na) rbound = __ldg(p.rowbound + (int64_t)b * p.row_chunks + rc);
     }
 
-    const int chunks_total = p.nb_pad / kChunk;
-    const int cps = (chunks_total + p.splits - 1) / p.splits;
-    const int chunk0 = split * cps;
-    const int nchunks = min(cps, chunks_total - chunk0);
-    const int ntiles = (nchunks + C::kTileChunks - 1) / C::kTileChunks;
-    const float* __restrict__ tp = p.b_packed + (int64_t)b * p.nb_pad * 3 + (int64_t)chunk0 * kChunk * 3;
-    u64* __restrict__ keys_col = p.keys_b + (int64_t)b * p.nb;
-    const unsigned colchunk_base = (unsigned)(qbase / C::kColChunkPts);
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < kSymStages; ++s) mbar_init(&full_bar[s], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    unsigned cmax = 0u;                                      // largest finite column minimum this thread merged
-
-    const float* __restrict__ bp = CULL ? p.colbox + ((int64_t)b * chunks_total + chunk0) * kBoxFloats : nullptr;
-    auto issue = [&](int k) {
-        const int st = k % kSymStages;
-        const int nch = min(C::kTileChunks, nchunks - k * C::kTileChunks);
-        const uint32_t bytes = (uint32_t)nch * kChunk * 12;
-        const uint32_t box_bytes = CULL ? (uint32_t)nch * kBoxFloats * 4 : 0u;
-        mbar_expect_tx(&full_bar[st], bytes + box_bytes);
-        tma_bulk_g2s(smem_raw + st * C::kTileBytes, tp + (int64_t)k * C::kTilePoints * 3, bytes, &full_bar[st]);
-        if (CULL)
-            tma_bulk_g2s(sbox + st * C::kTileChunks * kBoxFloats, bp + (int64_t)k * C::kTileChunks * kBoxFloats, box_bytes,
-                         &full_bar[st]);
-    };
-    if (tid == 0) {
-        for (int k = 0; k < min(kSymStages, ntiles); ++k) issue(k);
-    }
+    __syncthreads();                                         // barrier initialisation visible to every waiter
 
     for (int k = 0; k < ntiles; ++k) {
         const int st = k % kSymStages;

@@ -305,4 +305,52 @@ __device__ __forceinline__ int fixed_point_exponent(unsigned bound_bits, float g
     return max(-100, min(100, 61 - e));
 }
 
+// ----------------------------------------------------------------------------- seg MLP forward, shared by segmlp.cu / relax.cu
+// logits = W2 relu(W0 x + b0) for ONE point by kMlpLanes consecutive lanes of a warp: lane l covers the hidden units
+// k = l, l + kMlpLanes, ...; partial logits meet through xor shuffles, after which every lane of the point holds all of
+// them.  s0 [H][4] = (w0 row, bias), s2 [H][kS2] = W2 transposed, zero padded (kS2 = PMAX + 4 keeps float4 alignment and
+// spreads the transposing stores over the banks).  Both kernels use this one function, so their logits agree bit for bit.
+constexpr int kMlpLanes = 8;
+
+template <int PMAX>
+__device__ __forceinline__ void segmlp_stage(const float* __restrict__ w0, const float* __restrict__ b0,
+                                             const float* __restrict__ w2, int H, int P, float* __restrict__ s0,
+                                             float* __restrict__ s2) {
+    constexpr int kS2 = PMAX + 4;
+    for (int e = threadIdx.x; e < H; e += blockDim.x) {
+        s0[4 * e] = w0[3 * e]; s0[4 * e + 1] = w0[3 * e + 1]; s0[4 * e + 2] = w0[3 * e + 2]; s0[4 * e + 3] = b0[e];
+    }
+    for (int e = threadIdx.x; e < P * H; e += blockDim.x) {      // coalesced over the [P][H] weights
+        const int p = e / H, k = e - p * H;
+        s2[k * kS2 + p] = w2[e];
+    }
+    for (int e = threadIdx.x; e < H * (kS2 - P); e += blockDim.x) {
+        const int k = e / (kS2 - P), p = P + (e - k * (kS2 - P));
+        s2[k * kS2 + p] = 0.f;
+    }
+}
+
+template <int PMAX>
+__device__ __forceinline__ void segmlp_point(const float* __restrict__ s0, const float* __restrict__ s2, int H, int part,
+                                             float px, float py, float pz, float (&acc)[PMAX]) {
+    constexpr int kS2 = PMAX + 4;
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p) acc[p] = 0.f;
+    for (int k = part; k < H; k += kMlpLanes) {
+        const float4 w = reinterpret_cast<const float4*>(s0)[k];
+        const float h = fmaxf(w.x * px + w.y * py + w.z * pz + w.w, 0.f);
+        const float4* c4 = reinterpret_cast<const float4*>(s2 + k * kS2);
+#pragma unroll
+        for (int q = 0; q < PMAX / 4; ++q) {
+            const float4 c = c4[q];
+            acc[4 * q] += c.x * h; acc[4 * q + 1] += c.y * h; acc[4 * q + 2] += c.z * h; acc[4 * q + 3] += c.w * h;
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < PMAX; ++p) {
+#pragma unroll
+        for (int o = 1; o < kMlpLanes; o <<= 1) acc[p] += __shfl_xor_sync(0xffffffffu, acc[p], o);
+    }
+}
+
 }  // namespace reart

@@ -18,7 +18,7 @@
 namespace reart {
 
 // ============================================================================================ head
-constexpr int kHeadThreads = 256;                            // 4 lanes per point -> 64 points per block
+constexpr int kHeadThreads = 256;                            // kMlpLanes = 8 lanes per point -> 32 points per block
 
 template <int PMAX>
 __global__ void __launch_bounds__(kHeadThreads) relax_head_kernel(const float* __restrict__ x,
@@ -46,67 +46,61 @@ __global__ void __launch_bounds__(kHeadThreads) relax_head_kernel(const float* _
     }
     extern __shared__ __align__(16) float sm[];
     float* s0 = sm;                       // [H][4]: w0 row + bias
-    float* s2 = sm + H * 4;               // [H][PMAX]: W2 transposed, zero padded
-    for (int e = threadIdx.x; e < H; e += blockDim.x) {
-        s0[4 * e] = w0[3 * e]; s0[4 * e + 1] = w0[3 * e + 1]; s0[4 * e + 2] = w0[3 * e + 2]; s0[4 * e + 3] = b0[e];
-    }
-    for (int e = threadIdx.x; e < H * PMAX; e += blockDim.x) {
-        const int k = e / PMAX, p = e - k * PMAX;
-        s2[e] = p < P ? w2[p * H + k] : 0.f;
-    }
+    float* s2 = sm + H * 4;               // [H][PMAX + 4]: W2 transposed, zero padded
+    segmlp_stage<PMAX>(w0, b0, w2, H, P, s0, s2);
     __syncthreads();
-    // seg MLP: 4 lanes per point, each a quarter of the hidden units; partial logits meet through two shuffles
-    // (the arithmetic and its order are those of segmlp_fwd_kernel, so both paths give the same logits)
+    // seg MLP: kMlpLanes lanes per point (the function segmlp_fwd_kernel uses, so both paths give the same logits)
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = gid >> 2, part = gid & 3;
+    const int n = gid / kMlpLanes, part = gid % kMlpLanes;
     const bool real = n < N;
     float px = 0.f, py = 0.f, pz = 0.f;
     if (real) { px = x[3 * n]; py = x[3 * n + 1]; pz = x[3 * n + 2]; }
     float acc[PMAX];
-#pragma unroll
-    for (int p = 0; p < PMAX; ++p) acc[p] = 0.f;
-    for (int k = part; k < H; k += 4) {
-        const float4 w = reinterpret_cast<const float4*>(s0)[k];
-        const float h = fmaxf(w.x * px + w.y * py + w.z * pz + w.w, 0.f);
-        const float4* c4 = reinterpret_cast<const float4*>(s2 + k * PMAX);
-#pragma unroll
-        for (int q = 0; q < PMAX / 4; ++q) {
-            const float4 c = c4[q];
-            acc[4 * q] += c.x * h; acc[4 * q + 1] += c.y * h; acc[4 * q + 2] += c.z * h; acc[4 * q + 3] += c.w * h;
-        }
-    }
-#pragma unroll
-    for (int p = 0; p < PMAX; ++p) {
-        acc[p] += __shfl_xor_sync(0xffffffffu, acc[p], 1);
-        acc[p] += __shfl_xor_sync(0xffffffffu, acc[p], 2);
-    }
-    if (!real) return;
-    // straight-through gumbel softmax: every lane of the point evaluates the (tiny) softmax, each writes its parts
+    segmlp_point<PMAX>(s0, s2, H, part, px, py, pz, acc);
+    // straight-through gumbel softmax.  The transcendental work is SPLIT over the point's lanes (lane l evaluates the
+    // parts p = l, l + kMlpLanes, ...), the values are gathered back with shuffles and then summed / compared in part
+    // order by every lane -- the arithmetic and its order are those of gumbel_st_kernel, so W and ysoft agree bit for bit.
     const float inv_tau = 1.0f / *tau_ptr;
     // noise row of this point: its own, or (point order changed by the caller, e.g. the engine's k-d order) the row the
     // point had in the order the noise was drawn for -- the optimisation then takes the same random decisions
-    const int64_t nrow = noise_index ? noise_index[n] : (int64_t)n;
-    float z[PMAX];
+    const int64_t nrow = real ? (noise_index ? noise_index[n] : (int64_t)n) : 0;
+    constexpr int kOwn = (PMAX + kMlpLanes - 1) / kMlpLanes;
+    float zown[kOwn];
     float mx = -INFINITY;
 #pragma unroll
-    for (int p = 0; p < PMAX; ++p) {
-        if (p < P) {
-            z[p] = (acc[p] - logf(expo[nrow * P + p])) * inv_tau;
-            mx = fmaxf(mx, z[p]);
+    for (int q = 0; q < kOwn; ++q) {
+        const int p = part + q * kMlpLanes;
+        zown[q] = -INFINITY;
+        if (real && p < P) {
+            float a = 0.f;
+#pragma unroll
+            for (int pp = 0; pp < PMAX; ++pp) if (pp == p) a = acc[pp];           // register select (no dynamic indexing)
+            zown[q] = (a - logf(expo[nrow * P + p])) * inv_tau;
+            mx = fmaxf(mx, zown[q]);
         }
     }
+#pragma unroll
+    for (int o = 1; o < kMlpLanes; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+#pragma unroll
+    for (int q = 0; q < kOwn; ++q) zown[q] = expf(zown[q] - mx);                   // -inf slots -> 0, never read
+    const int lane0 = (threadIdx.x & 31) & ~(kMlpLanes - 1);                      // first lane of this point's group
+    float z[PMAX];
     float sum = 0.f;
 #pragma unroll
-    for (int p = 0; p < PMAX; ++p)
-        if (p < P) { z[p] = expf(z[p] - mx); sum += z[p]; }
+    for (int p = 0; p < PMAX; ++p) {
+        const float v = __shfl_sync(0xffffffffu, zown[p / kMlpLanes], lane0 + (p % kMlpLanes));
+        z[p] = v;
+        if (p < P) sum += v;
+    }
     int hot = 0;
     float best = -1.f;
 #pragma unroll
     for (int p = 0; p < PMAX; ++p)
         if (p < P) { z[p] = z[p] / sum; if (z[p] > best) { best = z[p]; hot = p; } }
+    if (!real) return;
 #pragma unroll
     for (int p = 0; p < PMAX; ++p) {
-        if (p < P && (p & 3) == part) {
+        if (p < P && (p % kMlpLanes) == part) {
             const float y = z[p];
             if (logits) logits[(int64_t)n * P + p] = acc[p];
             ysoft[(int64_t)n * P + p] = y;
@@ -120,11 +114,11 @@ int launch_relax_head(const float* cano, const float* w0, const float* b0, const
                       float* W, float* ysoft, float* R, cudaStream_t stream) {
     if (N <= 0 && T <= 0) return kOk;
     if (H <= 0 || H > 1024 || P <= 0 || P > 32) return kErrUnsupported;
-    const int point_blocks = (int)ceil_div(4 * N, kHeadThreads);
+    const int point_blocks = (int)ceil_div(kMlpLanes * N, kHeadThreads);
     const int pose_blocks = (int)ceil_div(T * P, kHeadThreads);
 #define REART_HEAD(PM)                                                                                               \
     do {                                                                                                             \
-        const size_t smem = (size_t)H * (4 + PM) * sizeof(float);                                                    \
+        const size_t smem = (size_t)H * (4 + PM + 4) * sizeof(float);                                                \
         if (smem > 48 * 1024) return kErrUnsupported;                                                                \
         relax_head_kernel<PM><<<(unsigned)(point_blocks + pose_blocks), kHeadThreads, smem, stream>>>(               \
             cano, w0, b0, w2, expo, noise_index, tau, d6, (int)N, (int)H, (int)P, (int)(T * P), point_blocks, logits, W, ysoft, R); \
@@ -367,15 +361,13 @@ __global__ void __launch_bounds__(1024) relax_tail_kernel(const RelaxTail a, int
             __threadfence();
             for (int e = tid; e < nseg; e += blockDim.x) {
                 float sacc = 0.f;
-                int c = 0;
-                for (; c + 8 <= ngroups; c += 8) {
-                    float v[8];
+                for (int c = 0; c < ngroups; c += 16) {          // 16 loads in flight, added in group order
+                    float v[16];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = __ldcg(gpart + (int64_t)(c + i) * nseg + e);
+                    for (int i = 0; i < 16; ++i) v[i] = c + i < ngroups ? __ldcg(gpart + (int64_t)(c + i) * nseg + e) : 0.f;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) sacc += v[i];
+                    for (int i = 0; i < 16; ++i) sacc += v[i];
                 }
-                for (; c < ngroups; ++c) sacc += __ldcg(gpart + (int64_t)c * nseg + e);
                 a.bucket[e] = sacc;
             }
             if (tid == 0) a.bucket[nseg] = (float)*reinterpret_cast<const volatile double*>(a.loss_local);

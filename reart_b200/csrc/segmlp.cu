@@ -13,10 +13,10 @@
 
 namespace reart {
 
-constexpr int kMlpThreads = 128;
+constexpr int kMlpThreads = 256;
 
 // ----------------------------------------------------------------------------- seg MLP forward
-// W0|b0 and W2^T staged in shared memory (broadcast reads)
+// W0|b0 and W2^T staged in shared memory; kMlpLanes lanes per point (common.cuh segmlp_point)
 template <int PMAX>
 __global__ void __launch_bounds__(kMlpThreads) segmlp_fwd_kernel(const float* __restrict__ x,
                                                                  const float* __restrict__ w0,
@@ -25,43 +25,20 @@ __global__ void __launch_bounds__(kMlpThreads) segmlp_fwd_kernel(const float* __
                                                                  float* __restrict__ logits) {
     extern __shared__ __align__(16) float sm[];
     float* s0 = sm;                       // [H][4]: w0 row + bias
-    float* s2 = sm + H * 4;               // [H][PMAX]: W2 transposed, zero padded
-    for (int e = threadIdx.x; e < H; e += blockDim.x) {
-        s0[4 * e] = w0[3 * e]; s0[4 * e + 1] = w0[3 * e + 1]; s0[4 * e + 2] = w0[3 * e + 2]; s0[4 * e + 3] = b0[e];
-    }
-    for (int e = threadIdx.x; e < H * PMAX; e += blockDim.x) {
-        const int k = e / PMAX, p = e - k * PMAX;
-        s2[e] = p < P ? w2[p * H + k] : 0.f;
-    }
+    float* s2 = sm + H * 4;               // [H][PMAX + 4]: W2 transposed, zero padded
+    segmlp_stage<PMAX>(w0, b0, w2, H, P, s0, s2);
     __syncthreads();
-    // 4 lanes per point, each covering a quarter of the hidden units; partial logits meet through two shuffles
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = gid >> 2, part = gid & 3;
+    const int n = gid / kMlpLanes, part = gid % kMlpLanes;
     const bool real = n < N;
     float px = 0.f, py = 0.f, pz = 0.f;
     if (real) { px = x[3 * n]; py = x[3 * n + 1]; pz = x[3 * n + 2]; }
     float acc[PMAX];
-#pragma unroll
-    for (int p = 0; p < PMAX; ++p) acc[p] = 0.f;
-    for (int k = part; k < H; k += 4) {
-        const float4 w = reinterpret_cast<const float4*>(s0)[k];
-        const float h = fmaxf(w.x * px + w.y * py + w.z * pz + w.w, 0.f);
-        const float4* c4 = reinterpret_cast<const float4*>(s2 + k * PMAX);
-#pragma unroll
-        for (int q = 0; q < PMAX / 4; ++q) {
-            const float4 c = c4[q];
-            acc[4 * q] += c.x * h; acc[4 * q + 1] += c.y * h; acc[4 * q + 2] += c.z * h; acc[4 * q + 3] += c.w * h;
-        }
-    }
-#pragma unroll
-    for (int p = 0; p < PMAX; ++p) {
-        acc[p] += __shfl_xor_sync(0xffffffffu, acc[p], 1);
-        acc[p] += __shfl_xor_sync(0xffffffffu, acc[p], 2);
-    }
+    segmlp_point<PMAX>(s0, s2, H, part, px, py, pz, acc);
     if (real) {
 #pragma unroll
         for (int p = 0; p < PMAX; ++p)
-            if (p < P && (p & 3) == part) logits[(int64_t)n * P + p] = acc[p];
+            if (p < P && (p % kMlpLanes) == part) logits[(int64_t)n * P + p] = acc[p];
     }
 }
 
@@ -121,9 +98,9 @@ static int launch_segmlp_p(const float* x, const float* w0, const float* b0, con
                            int64_t N, int64_t H, int64_t P, float* logits, float* gw0, float* gb0, float* gw2,
                            cudaStream_t stream) {
     if (logits) {
-        const size_t smem = (size_t)H * (4 + PMAX) * sizeof(float);
+        const size_t smem = (size_t)H * (4 + PMAX + 4) * sizeof(float);
         if (smem > 48 * 1024) return kErrUnsupported;
-        segmlp_fwd_kernel<PMAX><<<(unsigned)ceil_div(4 * N, kMlpThreads), kMlpThreads, smem, stream>>>(
+        segmlp_fwd_kernel<PMAX><<<(unsigned)ceil_div(kMlpLanes * N, kMlpThreads), kMlpThreads, smem, stream>>>(
             x, w0, b0, w2, (int)N, (int)H, (int)P, logits);
         REART_CHECK_LAUNCH();
         return kOk;

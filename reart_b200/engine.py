@@ -171,11 +171,14 @@ class RelaxationEngine(_EngineBase):
         self.total_frames = int(frames.shape[0])
         self.cano = cano.float().contiguous()
         self.frames = frames[lo:hi].float().contiguous()          # local shard of the observed frames
-        # Exact tile culling (csrc/cull.cu): on by default for the native fused iteration.  The loss is invariant to the
+        # Exact tile culling (csrc/cull.cu), opt-in (cull=True; native fused iteration only).  The loss is invariant to the
         # order of the points inside a cloud, so both clouds are put into k-d leaf order ONCE here (256-point leaves for
         # the canonical cloud = one warp of the search, 32-point leaves for the observed frames = one target chunk);
         # ``perm_cano`` / ``perm_frames`` map engine order -> caller order (engine.skinned[:, k] is caller point perm_cano[k]).
-        self.cull = (flow_ref is None and native is not False) if cull is None else bool(cull)
+        # The brute-force search stays the default: it is the kernel the roofline is quoted on and the order-preserving path.
+        self.cull = bool(cull) if cull is not None else False
+        if self.cull and (flow_ref is not None or native is False):
+            raise ValueError("exact tile culling runs on the native fused iteration (recon / assignment losses)")
         self.perm_cano = self.perm_frames = None
         cano_orig, frames_orig = self.cano, self.frames
         if self.cull:

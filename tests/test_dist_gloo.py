@@ -77,7 +77,7 @@ def test_two_rank_frame_sharding_reproduces_single_rank_energy(tmp_path):
     gW, _, _ = oracle.skin_bwd(seq["cano"], W, R, tr, ch["grad_src"])
     for r in (r0, r1):
         assert abs(float(r["loss"]) - ch["loss"]) <= 1e-5 * ch["loss"]              # summed over ranks
-        np.testing.assert_allclose(r["gW"], gW, rtol=1e-4, atol=1e-5 * np.abs(gW).max())
+        assert np.abs(r["gW"] - gW).max() <= 1e-5 * np.abs(gW).max()                 # max-norm relative (sum order differs)
     assert np.array_equal(r0["gW"], r1["gW"])                                       # all-reduce => identical
     # candidate selection: both ranks agree on the argmin of the gathered energies
     e = r0["energies"]

@@ -20,6 +20,16 @@ def dev():
     return torch.device("cuda")
 
 
+def assert_grad_close(got, want, tol):
+    """Gradient parity in the max norm: max|got - want| <= tol * max|want|  (profiles/r02_grad_fp64.md: against a float64
+    evaluation the reference's own float32 gradients sit at up to 1.9e-5 in this norm on its demo data, ours at 1.4e-5)."""
+    got = got.detach().cpu().numpy() if torch.is_tensor(got) else np.asarray(got)
+    want = want.detach().cpu().numpy() if torch.is_tensor(want) else np.asarray(want)
+    scale = float(np.abs(want).max())
+    assert float(np.abs(got - want).max()) <= tol * max(scale, 1e-30), (float(np.abs(got - want).max()), scale)
+
+
+
 def cu(a, dtype=None):
     t = torch.from_numpy(np.ascontiguousarray(a)).to(dev())
     return t if dtype is None else t.to(dtype)
@@ -289,7 +299,7 @@ def test_kinematic_model_kat_c(nao):
     loss.backward()
     for got, want in ((model.axis_list.grad, g["katC_g_axis"]), (model.moment_list.grad, g["katC_g_moment"]),
                       (model.theta_list.grad, g["katC_g_theta"])):
-        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+        assert_grad_close(got, want, 4e-5)                       # reference golden (CPU torch f32)
 
 
 def test_base_model_kat_d(nao):
@@ -331,7 +341,7 @@ def test_base_model_kat_d(nao):
     loss.backward()
     for got, want in ((model.proposal_6d.grad, g["katD_g_6d"]), (model.proposal_t.grad, g["katD_g_t"]),
                       (W.grad[::8], g["katD_g_W_s8"])):
-        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+        assert_grad_close(got, want, 4e-5)                       # reference golden (CPU torch f32)
 
 
 # ----------------------------------------------------------------------------------------- fused energy
@@ -357,14 +367,14 @@ def test_fused_energy_equals_composed_path_and_oracle(T, N, P):
     np.testing.assert_allclose(skinned.detach().cpu().numpy(), sk_ref, rtol=RTOL, atol=1e-6)
     assert abs(loss.item() - ch["loss"]) <= 2 * RTOL * ch["loss"]
     for got, want in ((Wt.grad, gW_ref), (Rt.grad, gR_ref), (trt.grad, gt_ref)):
-        np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+        assert_grad_close(got, want, 1e-5)                       # C oracle (same float32 arithmetic, other summation order)
     # composed autograd path gives the same numbers
     W2, R2, t2 = cu(W).requires_grad_(True), cu(R.astype(np.float32)).requires_grad_(True), cu(tr).requires_grad_(True)
     loss2 = ChamferDistance()(ops.skin(cu(cano), W2, R2, t2), cu(frames), bidirectional=True).sum()
     loss2.backward()
     assert abs(loss2.item() - loss.item()) <= RTOL * abs(loss.item())
-    np.testing.assert_allclose(W2.grad.cpu().numpy(), Wt.grad.cpu().numpy(), rtol=1e-4, atol=1e-4 * float(Wt.grad.abs().max()))
-    np.testing.assert_allclose(R2.grad.cpu().numpy(), Rt.grad.cpu().numpy(), rtol=1e-4, atol=1e-4 * float(Rt.grad.abs().max()))
+    assert_grad_close(W2.grad, Wt.grad, 1e-5)
+    assert_grad_close(R2.grad, Rt.grad, 1e-5)
 
 
 def test_fused_energy_backward_is_bitwise_deterministic():
@@ -868,6 +878,50 @@ def test_oneshot_allreduce_matches_nccl_on_two_gpus(tmp_path):
     mp.spawn(_oneshot_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert float(np.load(tmp_path / "r0.npy")[0]) < 1e-5 and float(np.load(tmp_path / "r1.npy")[0]) < 1e-5
     assert np.array_equal(np.load(tmp_path / "y0.npy"), np.load(tmp_path / "y1.npy"))      # identical bits on both ranks
+
+
+def _sharded_engine_worker(rank, world, port, out_dir):
+    import os
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from reart_b200.dist import DistContext
+    from reart_b200.engine import RelaxationEngine, tau_schedule
+    ctx = DistContext.from_env()
+    d = torch.device("cuda", rank)
+    seq = synthetic_sequence(8, 4096, 6, seed=2)
+    cano, frames = torch.from_numpy(seq["cano"]).to(d), torch.from_numpy(seq["frames"]).to(d)
+    out = {}
+    for graph in (False, True):
+        eng = RelaxationEngine(cano, frames, 6, ctx=ctx, use_graph=graph, seed=2)
+        torch.manual_seed(5); torch.cuda.manual_seed_all(5)
+        out[f"sharded_{int(graph)}"] = [float(eng.step(tau_schedule(i, 100, 5.0, 1.0))) for i in range(10)]
+        out[f"w2_{int(graph)}"] = eng.model.seg_head.model[2].weight.detach().cpu().numpy().copy()
+        eng.release()
+    if rank == 0:
+        single = RelaxationEngine(cano, frames, 6, ctx=DistContext(), use_graph=False, seed=2)
+        torch.manual_seed(5); torch.cuda.manual_seed_all(5)
+        out["single"] = [float(single.step(tau_schedule(i, 100, 5.0, 1.0))) for i in range(10)]
+    np.savez(os.path.join(out_dir, f"eng{rank}.npz"), **out)
+    dist.barrier()
+    os._exit(0)
+
+
+@pytest.mark.timeout(300)
+def test_sharded_native_engine_on_two_gpus(tmp_path):
+    """Frame sharding with the all-reduce fused into relax_tail_kernel (peer memory): the sharded step reproduces the
+    single-GPU step (first step to 1e-6: only the association of the frame sums differs), a captured graph replays the
+    eager sharded optimisation bit for bit, and both ranks hold bit-identical shared parameters."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_sharded_engine_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "eng0.npz"), np.load(tmp_path / "eng1.npz")
+    assert list(r0["sharded_0"]) == list(r0["sharded_1"]) == list(r1["sharded_0"]) == list(r1["sharded_1"])
+    assert np.array_equal(r0["w2_1"], r1["w2_1"]) and np.array_equal(r0["w2_0"], r0["w2_1"])
+    assert abs(r0["sharded_0"][0] - r0["single"][0]) <= 1e-6 * r0["single"][0]
+    np.testing.assert_allclose(r0["sharded_0"], r0["single"], rtol=5e-3)
 
 
 def test_register_blocked_topk_and_blend_path_vs_oracle():
