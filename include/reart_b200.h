@@ -251,6 +251,10 @@ REART_API int reart_fk_bwd(const float* axis, const float* moment, const float* 
  * ------------------------------------------------------------------------------------------- */
 REART_API int reart_knn(const float* ref, const float* query, int64_t B, int64_t n, int64_t m, int k, float* dist,
                         int64_t* idx, void* stream);
+/* The same search returning SQUARED distances (the chamferdist._C.knn_points_idx contract for K > 1,
+ * utils/chamfer.py:174-189; the reference itself only ever uses K == 1). */
+REART_API int reart_knn_sq(const float* ref, const float* query, int64_t B, int64_t n, int64_t m, int k, float* dist,
+                           int64_t* idx, void* stream);
 
 /* Flow blending for all frame pairs at once.  Replaces the Python loop over
  * blend_anchor_motion(query, ref, flow, knn_flow, return_mask=True) (utils/flow_utils.py:147-170,

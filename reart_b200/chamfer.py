@@ -201,14 +201,17 @@ def knn_points(
     if K == 1:
         p1_dists, p1_idx = _Knn1.apply(p1, p2)
     else:
-        # K > 1 is never used by the reference: indices from the small-k kernel (ascending, lowest index on ties);
-        # the squared distances are re-formed in torch from the gathered neighbours, which also gives autograd
+        # K > 1 is never used by the reference: indices AND squared distances from the small-k kernel (ascending, lowest
+        # index on ties -- the _C contract); when a gradient is needed the same distances re-formed in torch from the
+        # gathered neighbours carry the autograd graph, the returned VALUES stay the kernel's
         from . import ops
         if p2.shape[1] < K:
             raise ValueError("knn_points: fewer than K points in p2")
-        _, p1_idx = ops.knn(p2, p1, K)
-        nbrs = knn_gather(p2, p1_idx)
-        p1_dists = ((p1[:, :, None, :] - nbrs) ** 2).sum(-1)
+        p1_dists, p1_idx = ops.knn(p2, p1, K, squared=True)
+        if torch.is_grad_enabled() and (p1.requires_grad or p2.requires_grad):
+            nbrs = knn_gather(p2, p1_idx)
+            soft = ((p1[:, :, None, :] - nbrs) ** 2).sum(-1)
+            p1_dists = p1_dists + (soft - soft.detach())
     p2_nn = None
     if return_nn:
         p2_nn = knn_gather(p2, p1_idx, lengths2)

@@ -463,7 +463,17 @@ int reart_knn(const float* ref, const float* query, int64_t B, int64_t n, int64_
     if (B == 0 || m == 0) return REART_OK;
     if (n < k) return REART_ERR_INVALID_ARG;
     if (!ref || !query || !dist || !idx) return REART_ERR_INVALID_ARG;
-    return launch_knn(ref, query, B, n, m, k, dist, idx, static_cast<cudaStream_t>(stream_));
+    return launch_knn(ref, query, B, n, m, k, dist, idx, 0, static_cast<cudaStream_t>(stream_));
+}
+
+int reart_knn_sq(const float* ref, const float* query, int64_t B, int64_t n, int64_t m, int k, float* dist, int64_t* idx,
+                 void* stream_) {
+    REART_ENTRY();
+    if (B < 0 || n < 0 || m < 0 || k < 1 || k > 8 || !fits_int(n) || !fits_int(m)) return REART_ERR_INVALID_ARG;
+    if (B == 0 || m == 0) return REART_OK;
+    if (n < k) return REART_ERR_INVALID_ARG;
+    if (!ref || !query || !dist || !idx) return REART_ERR_INVALID_ARG;
+    return launch_knn(ref, query, B, n, m, k, dist, idx, 1, static_cast<cudaStream_t>(stream_));
 }
 
 int reart_knn3_blend(const float* query, const float* ref_cat, const float* flow_cat, const int64_t* ref_offsets,

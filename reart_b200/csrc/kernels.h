@@ -134,7 +134,7 @@ int energy_max_blocks();
 int launch_energy_bwd(const EnergyParams& p, cudaStream_t stream);
 
 int launch_knn(const float* ref, const float* query, int64_t B, int64_t n, int64_t m, int k, float* dist, int64_t* idx,
-               cudaStream_t stream);
+               int squared, cudaStream_t stream);
 int launch_knn3_blend(const float* query, const float* ref_cat, const float* flow_cat, const int64_t* ref_off,
                       int64_t T, int64_t m, float* blended, unsigned char* mask, cudaStream_t stream);
 

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_topk_kernel(const float* __re
                                                                float* __restrict__ out_dist,
                                                                int64_t* __restrict__ out_idx,
                                                                float* __restrict__ out_blend,
-                                                               unsigned char* __restrict__ out_mask) {
+                                                               unsigned char* __restrict__ out_mask, int squared) {
     __shared__ float sx[kKnnTile], sy[kKnnTile], sz[kKnnTile];
     const int b = blockIdx.y;
     const int64_t r0 = ref_off ? ref_off[b] : (int64_t)b * n_dense;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_topk_kernel(const float* __re
     const int64_t o = (int64_t)b * m + i;
     if (!BLEND) {
 #pragma unroll
-        for (int a = 0; a < K; ++a) { out_dist[o * K + a] = sqrtf(bd[a]); out_idx[o * K + a] = bi[a]; }
+        for (int a = 0; a < K; ++a) { out_dist[o * K + a] = squared ? bd[a] : sqrtf(bd[a]); out_idx[o * K + a] = bi[a]; }
     } else {
         // utils/flow_utils.py:159-167
         float w[K], ws = 0.f, mind = INFINITY, maxf = -INFINITY;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kTkThreads) knn_topk_tiled_kernel(const float*
                                                                     int m, float* __restrict__ out_dist,
                                                                     int64_t* __restrict__ out_idx,
                                                                     float* __restrict__ out_blend,
-                                                                    unsigned char* __restrict__ out_mask) {
+                                                                    unsigned char* __restrict__ out_mask, int squared) {
     __shared__ __align__(16) float tile[kTkTile * 3];          // groups of 4: [x0..x3|y0..y3|z0..z3]
     const int b = blockIdx.y;
     const int64_t r0 = ref_off ? ref_off[b] : (int64_t)b * n_dense;
@@ -147,22 +147,56 @@ __global__ void __launch_bounds__(kTkThreads) knn_topk_tiled_kernel(const float*
         }
         __syncthreads();
         const float4* __restrict__ t4 = reinterpret_cast<const float4*>(tile);
-        for (int g = 0; g < cnt4 / 4; ++g) {
-            const float4 X = t4[3 * g], Y = t4[3 * g + 1], Z = t4[3 * g + 2];
-            const u64 X01 = pack2(X.x, X.y), X23 = pack2(X.z, X.w);
-            const u64 Y01 = pack2(Y.x, Y.y), Y23 = pack2(Y.z, Y.w);
-            const u64 Z01 = pack2(Z.x, Z.y), Z23 = pack2(Z.z, Z.w);
+        // Phase A: branch-free sweep of the tile.  Per query only ONE bit per group of four references is kept: "the
+        // smallest of the four fresh distances beats the K-th best this query had when the tile started".  (Round 1
+        // inserted on the spot: the warp then ran the sorted insertion whenever ANY of its 32 lanes triggered, ~a third of
+        // all groups, which cost as much as the sweep itself.)
+        unsigned trig[kTkRQ][kTkTile / 128];
+        float kth[kTkRQ];
 #pragma unroll
-            for (int r = 0; r < kTkRQ; ++r) {
-                float a0, a1, a2, a3;
-                unpack2(sqdist_pair(QX[r], QY[r], QZ[r], X01, Y01, Z01), a0, a1);
-                unpack2(sqdist_pair(QX[r], QY[r], QZ[r], X23, Y23, Z23), a2, a3);
-                if (fminf(min3(a0, a1, a2), a3) < bd[r][K - 1]) {
+        for (int r = 0; r < kTkRQ; ++r) {
+            kth[r] = bd[r][K - 1];
+#pragma unroll
+            for (int w = 0; w < kTkTile / 128; ++w) trig[r][w] = 0u;
+        }
+        const int ngroups = cnt4 / 4;
+#pragma unroll
+        for (int w = 0; w < kTkTile / 128; ++w) {
+            const int gend = min(32, ngroups - 32 * w);
+            for (int gg = 0; gg < gend; ++gg) {
+                const int g = 32 * w + gg;
+                const float4 X = t4[3 * g], Y = t4[3 * g + 1], Z = t4[3 * g + 2];
+                const u64 X01 = pack2(X.x, X.y), X23 = pack2(X.z, X.w);
+                const u64 Y01 = pack2(Y.x, Y.y), Y23 = pack2(Y.z, Y.w);
+                const u64 Z01 = pack2(Z.x, Z.y), Z23 = pack2(Z.z, Z.w);
+#pragma unroll
+                for (int r = 0; r < kTkRQ; ++r) {
+                    float a0, a1, a2, a3;
+                    unpack2(sqdist_pair(QX[r], QY[r], QZ[r], X01, Y01, Z01), a0, a1);
+                    unpack2(sqdist_pair(QX[r], QY[r], QZ[r], X23, Y23, Z23), a2, a3);
+                    trig[r][w] |= (fminf(min3(a0, a1, a2), a3) < kth[r] ? 1u : 0u) << gg;
+                }
+            }
+        }
+        // Phase B: only the flagged groups, in increasing index order (ties keep the lowest index first, as before); the
+        // distances are re-formed with the same arithmetic and offered to the sorted list with its usual strict test.
+#pragma unroll
+        for (int r = 0; r < kTkRQ; ++r) {
+            float qx, qy, qz, dummy;
+            unpack2(QX[r], qx, dummy); unpack2(QY[r], qy, dummy); unpack2(QZ[r], qz, dummy);
+#pragma unroll
+            for (int w = 0; w < kTkTile / 128; ++w) {
+                unsigned mbits = trig[r][w];
+                while (mbits) {
+                    const int gg = __ffs(mbits) - 1;
+                    mbits &= mbits - 1u;
+                    const int g = 32 * w + gg;
+                    const float4 X = t4[3 * g], Y = t4[3 * g + 1], Z = t4[3 * g + 2];
                     const int j = base + 4 * g;
-                    topk_insert<K>(bd[r], bi[r], a0, j);
-                    topk_insert<K>(bd[r], bi[r], a1, j + 1);
-                    topk_insert<K>(bd[r], bi[r], a2, j + 2);
-                    topk_insert<K>(bd[r], bi[r], a3, j + 3);
+                    topk_insert<K>(bd[r], bi[r], sqdist_scalar(qx, qy, qz, X.x, Y.x, Z.x), j);
+                    topk_insert<K>(bd[r], bi[r], sqdist_scalar(qx, qy, qz, X.y, Y.y, Z.y), j + 1);
+                    topk_insert<K>(bd[r], bi[r], sqdist_scalar(qx, qy, qz, X.z, Y.z, Z.z), j + 2);
+                    topk_insert<K>(bd[r], bi[r], sqdist_scalar(qx, qy, qz, X.w, Y.w, Z.w), j + 3);
                 }
             }
         }
@@ -174,7 +208,7 @@ __global__ void __launch_bounds__(kTkThreads) knn_topk_tiled_kernel(const float*
         const int64_t o = (int64_t)b * m + i;
         if (!BLEND) {
 #pragma unroll
-            for (int a = 0; a < K; ++a) { out_dist[o * K + a] = sqrtf(bd[r][a]); out_idx[o * K + a] = bi[r][a]; }
+            for (int a = 0; a < K; ++a) { out_dist[o * K + a] = squared ? bd[r][a] : sqrtf(bd[r][a]); out_idx[o * K + a] = bi[r][a]; }
         } else {
             float w[K], ws = 0.f, mind = INFINITY, maxf = -INFINITY;
             float fx[K], fy[K], fz[K];
@@ -203,34 +237,34 @@ __global__ void __launch_bounds__(kTkThreads) knn_topk_tiled_kernel(const float*
 
 template <int K>
 static int launch_knn_k(const float* ref, const float* query, int64_t B, int64_t n, int64_t m, float* dist,
-                        int64_t* idx, cudaStream_t stream) {
+                        int64_t* idx, int squared, cudaStream_t stream) {
     if (K <= 4 && m >= 2048) {                               // register-blocked packed-math variant for real workloads
         dim3 tg((unsigned)ceil_div(m, kTkThreads * kTkRQ), (unsigned)B);
         knn_topk_tiled_kernel<(K <= 4 ? K : 1), false><<<tg, kTkThreads, 0, stream>>>(ref, query, nullptr, nullptr, (int)n,
-                                                                                     (int)m, dist, idx, nullptr, nullptr);
+                                                                                     (int)m, dist, idx, nullptr, nullptr, squared);
         REART_CHECK_LAUNCH();
         return kOk;
     }
     dim3 grid((unsigned)ceil_div(m, kKnnThreads), (unsigned)B);
     knn_topk_kernel<K, false><<<grid, kKnnThreads, 0, stream>>>(ref, query, nullptr, nullptr, (int)n, (int)m, dist, idx,
-                                                                nullptr, nullptr);
+                                                                nullptr, nullptr, squared);
     REART_CHECK_LAUNCH();
     return kOk;
 }
 
 int launch_knn(const float* ref, const float* query, int64_t B, int64_t n, int64_t m, int k, float* dist, int64_t* idx,
-               cudaStream_t stream) {
+               int squared, cudaStream_t stream) {
     if (B <= 0 || m <= 0) return kOk;
     if (B > 65535) return kErrUnsupported;
     switch (k) {
-        case 1: return launch_knn_k<1>(ref, query, B, n, m, dist, idx, stream);
-        case 2: return launch_knn_k<2>(ref, query, B, n, m, dist, idx, stream);
-        case 3: return launch_knn_k<3>(ref, query, B, n, m, dist, idx, stream);
-        case 4: return launch_knn_k<4>(ref, query, B, n, m, dist, idx, stream);
-        case 5: return launch_knn_k<5>(ref, query, B, n, m, dist, idx, stream);
-        case 6: return launch_knn_k<6>(ref, query, B, n, m, dist, idx, stream);
-        case 7: return launch_knn_k<7>(ref, query, B, n, m, dist, idx, stream);
-        case 8: return launch_knn_k<8>(ref, query, B, n, m, dist, idx, stream);
+        case 1: return launch_knn_k<1>(ref, query, B, n, m, dist, idx, squared, stream);
+        case 2: return launch_knn_k<2>(ref, query, B, n, m, dist, idx, squared, stream);
+        case 3: return launch_knn_k<3>(ref, query, B, n, m, dist, idx, squared, stream);
+        case 4: return launch_knn_k<4>(ref, query, B, n, m, dist, idx, squared, stream);
+        case 5: return launch_knn_k<5>(ref, query, B, n, m, dist, idx, squared, stream);
+        case 6: return launch_knn_k<6>(ref, query, B, n, m, dist, idx, squared, stream);
+        case 7: return launch_knn_k<7>(ref, query, B, n, m, dist, idx, squared, stream);
+        case 8: return launch_knn_k<8>(ref, query, B, n, m, dist, idx, squared, stream);
         default: return kErrUnsupported;
     }
 }
@@ -242,13 +276,13 @@ int launch_knn3_blend(const float* query, const float* ref_cat, const float* flo
     if (m >= 2048) {
         dim3 tg((unsigned)ceil_div(m, kTkThreads * kTkRQ), (unsigned)T);
         knn_topk_tiled_kernel<3, true><<<tg, kTkThreads, 0, stream>>>(ref_cat, query, flow_cat, ref_off, 0, (int)m, nullptr,
-                                                                      nullptr, blended, mask);
+                                                                      nullptr, blended, mask, 0);
         REART_CHECK_LAUNCH();
         return kOk;
     }
     dim3 grid((unsigned)ceil_div(m, kKnnThreads), (unsigned)T);
     knn_topk_kernel<3, true><<<grid, kKnnThreads, 0, stream>>>(ref_cat, query, flow_cat, ref_off, 0, (int)m, nullptr,
-                                                               nullptr, blended, mask);
+                                                               nullptr, blended, mask, 0);
     REART_CHECK_LAUNCH();
     return kOk;
 }

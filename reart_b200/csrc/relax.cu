@@ -340,14 +340,28 @@ __global__ void __launch_bounds__(1024) relax_tail_kernel(const RelaxTail a, int
         if (last_grp) {
             __threadfence();
             const float* part = a.partials + (int64_t)g0 * nseg;
-            for (int e = tid; e < nseg; e += blockDim.x) {
-                float v[kTailGroup];
+            if ((nseg & 3) == 0) {                              // four outputs per thread and load: fewer dependent round trips
+                const int n4 = nseg >> 2;
+                for (int e = tid; e < n4; e += blockDim.x) {
+                    float4 v[kTailGroup];
 #pragma unroll
-                for (int c = 0; c < kTailGroup; ++c) v[c] = c < gn ? __ldcg(part + (int64_t)c * nseg + e) : 0.f;
-                float sacc = v[0];
+                    for (int c = 0; c < kTailGroup; ++c)
+                        v[c] = c < gn ? __ldcg(reinterpret_cast<const float4*>(part + (int64_t)c * nseg) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 sacc = v[0];
 #pragma unroll
-                for (int c = 1; c < kTailGroup; ++c) sacc += v[c];
-                gpart[(int64_t)grp * nseg + e] = sacc;
+                    for (int c = 1; c < kTailGroup; ++c) { sacc.x += v[c].x; sacc.y += v[c].y; sacc.z += v[c].z; sacc.w += v[c].w; }
+                    reinterpret_cast<float4*>(gpart + (int64_t)grp * nseg)[e] = sacc;
+                }
+            } else {
+                for (int e = tid; e < nseg; e += blockDim.x) {
+                    float v[kTailGroup];
+#pragma unroll
+                    for (int c = 0; c < kTailGroup; ++c) v[c] = c < gn ? __ldcg(part + (int64_t)c * nseg + e) : 0.f;
+                    float sacc = v[0];
+#pragma unroll
+                    for (int c = 1; c < kTailGroup; ++c) sacc += v[c];
+                    gpart[(int64_t)grp * nseg + e] = sacc;
+                }
             }
             __syncthreads();
             if (tid == 0) {
@@ -359,16 +373,33 @@ __global__ void __launch_bounds__(1024) relax_tail_kernel(const RelaxTail a, int
         if (last_pts) {
             // ---- the last group to finish: group sums -> bucket in group order, then [all-reduce], then Adam
             __threadfence();
-            for (int e = tid; e < nseg; e += blockDim.x) {
-                float sacc = 0.f;
-                for (int c = 0; c < ngroups; c += 16) {          // 16 loads in flight, added in group order
-                    float v[16];
+            if ((nseg & 3) == 0) {
+                const int n4 = nseg >> 2;
+                for (int e = tid; e < n4; e += blockDim.x) {
+                    float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int c = 0; c < ngroups; c += 16) {      // 16 loads in flight, added in group order
+                        float4 v[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = c + i < ngroups ? __ldcg(gpart + (int64_t)(c + i) * nseg + e) : 0.f;
+                        for (int i = 0; i < 16; ++i)
+                            v[i] = c + i < ngroups ? __ldcg(reinterpret_cast<const float4*>(gpart + (int64_t)(c + i) * nseg) + e)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) sacc += v[i];
+                        for (int i = 0; i < 16; ++i) { sacc.x += v[i].x; sacc.y += v[i].y; sacc.z += v[i].z; sacc.w += v[i].w; }
+                    }
+                    reinterpret_cast<float4*>(a.bucket)[e] = sacc;
                 }
-                a.bucket[e] = sacc;
+            } else {
+                for (int e = tid; e < nseg; e += blockDim.x) {
+                    float sacc = 0.f;
+                    for (int c = 0; c < ngroups; c += 16) {
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = c + i < ngroups ? __ldcg(gpart + (int64_t)(c + i) * nseg + e) : 0.f;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) sacc += v[i];
+                    }
+                    a.bucket[e] = sacc;
+                }
             }
             if (tid == 0) a.bucket[nseg] = (float)*reinterpret_cast<const volatile double*>(a.loss_local);
             __syncthreads();

@@ -297,8 +297,8 @@ def fk_flat(axis, moment, theta, distance, order, parent, edge, joint_type=None)
 
 # --------------------------------------------------------------------------------------- k-NN helpers (no grad)
 @torch.no_grad()
-def knn(ref: torch.Tensor, query: torch.Tensor, k: int):
-    """ref [B,n,3], query [B,m,3] -> (dist [B,m,k] Euclidean, idx [B,m,k] int64), ascending."""
+def knn(ref: torch.Tensor, query: torch.Tensor, k: int, squared: bool = False):
+    """ref [B,n,3], query [B,m,3] -> (dist [B,m,k] Euclidean -- or squared -- , idx [B,m,k] int64), ascending."""
     _lib.require_cuda(ref, query)
     L = _lib.lib()
     ref, query = _f32c(ref), _f32c(query)
@@ -306,8 +306,9 @@ def knn(ref: torch.Tensor, query: torch.Tensor, k: int):
     m = query.shape[1]
     dist = torch.empty(B, m, k, dtype=torch.float32, device=ref.device)
     idx = torch.empty(B, m, k, dtype=torch.int64, device=ref.device)
+    fn = L.reart_knn_sq if squared else L.reart_knn
     with torch.cuda.device(ref.device):
-        check(L.reart_knn(ptr(ref), ptr(query), B, n, m, int(k), ptr(dist), ptr(idx), stream_ptr()), "reart_knn")
+        check(fn(ptr(ref), ptr(query), B, n, m, int(k), ptr(dist), ptr(idx), stream_ptr()), "reart_knn")
     return dist, idx
 
 
