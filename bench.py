@@ -113,6 +113,10 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    try:        # the reference's own Python loop on the same cores (needs the staged copy baseline/_ref/reart), reported beside it
+        line["cpu_baseline_reference_python"] = reference_python_cpu_baseline(T, N, P)
+    except Exception as exc:
+        line["cpu_baseline_reference_python"] = {"error": f"{type(exc).__name__}: {exc}"}
     print(json.dumps(line), flush=True)
 
 

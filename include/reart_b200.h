@@ -295,6 +295,11 @@ REART_API int reart_assign_loss_grad(const float* skinned, const int64_t* src_id
  *   (idx must be zero-filled by the caller, as the reference does).
  * ------------------------------------------------------------------------------------------- */
 REART_API int reart_fps(const float* xyz, int64_t B, int64_t N, int64_t npoint, int32_t* out, void* stream);
+/* The wrapper's full signature (furthest_point_sampling_wrapper(B, N, npoint, xyz, temp, out),
+ * networks/pointnet_lib/pointnet2_utils.py:29): temp [B,N] float32 scratch lifts the N <= 32768 limit of reart_fps
+ * (clouds up to that size ignore it).  Same samples as reart_fps. */
+REART_API int reart_fps_temp(const float* xyz, int64_t B, int64_t N, int64_t npoint, float* temp, int32_t* out,
+                             void* stream);
 REART_API int reart_ball_query(const float* new_xyz, const float* xyz, int64_t B, int64_t N, int64_t m, float radius,
                                int nsample, int32_t* idx, void* stream);
 

@@ -57,6 +57,7 @@ SIGNATURES = {
     "reart_knn_sq": (_c_int, [_vp, _vp, _c_i64, _c_i64, _c_i64, _c_int, _vp, _vp, _vp]),
     "reart_knn3_blend": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_i64, _vp, _vp, _vp]),
     "reart_fps": (_c_int, [_vp, _c_i64, _c_i64, _c_i64, _vp, _vp]),
+    "reart_fps_temp": (_c_int, [_vp, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp]),
     "reart_ball_query": (_c_int, [_vp, _vp, _c_i64, _c_i64, _c_i64, ctypes.c_float, _c_int, _vp, _vp]),
     "reart_allreduce_oneshot": (_c_int, [_vp, _c_int, _c_int, _c_i64, _c_i64, _vp, _vp, _vp]),
     "reart_fp32_probe": (_c_int, [_c_int, _c_int, _c_int, _vp, _vp, ctypes.POINTER(ctypes.c_double),

@@ -516,6 +516,17 @@ int reart_fps(const float* xyz, int64_t B, int64_t N, int64_t npoint, int32_t* o
     return launch_fps(xyz, B, N, npoint, out, static_cast<cudaStream_t>(stream_));
 }
 
+int reart_fps_temp(const float* xyz, int64_t B, int64_t N, int64_t npoint, float* temp, int32_t* out, void* stream_) {
+    REART_ENTRY();
+    if (B < 0 || N < 0 || npoint < 0 || !fits_int(N)) return REART_ERR_INVALID_ARG;
+    if (B == 0 || npoint == 0) return REART_OK;
+    if (!xyz || !out || N == 0) return REART_ERR_INVALID_ARG;
+    // small clouds: the register kernel (temp unused); larger ones: running distances in the caller's temp [B,N]
+    if (N <= 32768) return launch_fps(xyz, B, N, npoint, out, static_cast<cudaStream_t>(stream_));
+    if (!temp) return REART_ERR_WORKSPACE;
+    return launch_fps_large(xyz, B, N, npoint, temp, out, static_cast<cudaStream_t>(stream_));
+}
+
 int reart_ball_query(const float* new_xyz, const float* xyz, int64_t B, int64_t N, int64_t m, float radius,
                      int nsample, int32_t* idx, void* stream_) {
     REART_ENTRY();

@@ -139,6 +139,7 @@ int launch_knn3_blend(const float* query, const float* ref_cat, const float* flo
                       int64_t T, int64_t m, float* blended, unsigned char* mask, cudaStream_t stream);
 
 int launch_fps(const float* xyz, int64_t B, int64_t N, int64_t m, int* out, cudaStream_t stream);
+int launch_fps_large(const float* xyz, int64_t B, int64_t N, int64_t m, float* temp, int* out, cudaStream_t stream);
 int launch_ball_query(const float* new_xyz, const float* xyz, int64_t B, int64_t N, int64_t m, float radius,
                       int nsample, int* idx, cudaStream_t stream);
 

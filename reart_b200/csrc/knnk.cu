@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(kKnnThreads) knn_topk_kernel(const float* __re
 // and the sorted top-K insertion only runs when the smallest of four fresh distances beats the query's current
 // K-th best (after the first few tiles that is rare).  Candidates are offered in increasing index order with a
 // strict <, so equal distances keep the lowest index first, exactly like the one-query-per-thread kernel.
+// (Round 2 tried a two-phase form -- branch-free sweep recording one trigger bit per group, insertion afterwards from the
+// bit masks -- and measured it SLOWER: 1.58 ms vs 1.22 ms on the 64-pair flow workload; the immediate form stays.)
 constexpr int kTkThreads = 128;
 constexpr int kTkRQ = 4;
 constexpr int kTkTile = 512;                                  // reference points per shared-memory tile
@@ -147,56 +149,22 @@ __global__ void __launch_bounds__(kTkThreads) knn_topk_tiled_kernel(const float*
         }
         __syncthreads();
         const float4* __restrict__ t4 = reinterpret_cast<const float4*>(tile);
-        // Phase A: branch-free sweep of the tile.  Per query only ONE bit per group of four references is kept: "the
-        // smallest of the four fresh distances beats the K-th best this query had when the tile started".  (Round 1
-        // inserted on the spot: the warp then ran the sorted insertion whenever ANY of its 32 lanes triggered, ~a third of
-        // all groups, which cost as much as the sweep itself.)
-        unsigned trig[kTkRQ][kTkTile / 128];
-        float kth[kTkRQ];
+        for (int g = 0; g < cnt4 / 4; ++g) {
+            const float4 X = t4[3 * g], Y = t4[3 * g + 1], Z = t4[3 * g + 2];
+            const u64 X01 = pack2(X.x, X.y), X23 = pack2(X.z, X.w);
+            const u64 Y01 = pack2(Y.x, Y.y), Y23 = pack2(Y.z, Y.w);
+            const u64 Z01 = pack2(Z.x, Z.y), Z23 = pack2(Z.z, Z.w);
 #pragma unroll
-        for (int r = 0; r < kTkRQ; ++r) {
-            kth[r] = bd[r][K - 1];
-#pragma unroll
-            for (int w = 0; w < kTkTile / 128; ++w) trig[r][w] = 0u;
-        }
-        const int ngroups = cnt4 / 4;
-#pragma unroll
-        for (int w = 0; w < kTkTile / 128; ++w) {
-            const int gend = min(32, ngroups - 32 * w);
-            for (int gg = 0; gg < gend; ++gg) {
-                const int g = 32 * w + gg;
-                const float4 X = t4[3 * g], Y = t4[3 * g + 1], Z = t4[3 * g + 2];
-                const u64 X01 = pack2(X.x, X.y), X23 = pack2(X.z, X.w);
-                const u64 Y01 = pack2(Y.x, Y.y), Y23 = pack2(Y.z, Y.w);
-                const u64 Z01 = pack2(Z.x, Z.y), Z23 = pack2(Z.z, Z.w);
-#pragma unroll
-                for (int r = 0; r < kTkRQ; ++r) {
-                    float a0, a1, a2, a3;
-                    unpack2(sqdist_pair(QX[r], QY[r], QZ[r], X01, Y01, Z01), a0, a1);
-                    unpack2(sqdist_pair(QX[r], QY[r], QZ[r], X23, Y23, Z23), a2, a3);
-                    trig[r][w] |= (fminf(min3(a0, a1, a2), a3) < kth[r] ? 1u : 0u) << gg;
-                }
-            }
-        }
-        // Phase B: only the flagged groups, in increasing index order (ties keep the lowest index first, as before); the
-        // distances are re-formed with the same arithmetic and offered to the sorted list with its usual strict test.
-#pragma unroll
-        for (int r = 0; r < kTkRQ; ++r) {
-            float qx, qy, qz, dummy;
-            unpack2(QX[r], qx, dummy); unpack2(QY[r], qy, dummy); unpack2(QZ[r], qz, dummy);
-#pragma unroll
-            for (int w = 0; w < kTkTile / 128; ++w) {
-                unsigned mbits = trig[r][w];
-                while (mbits) {
-                    const int gg = __ffs(mbits) - 1;
-                    mbits &= mbits - 1u;
-                    const int g = 32 * w + gg;
-                    const float4 X = t4[3 * g], Y = t4[3 * g + 1], Z = t4[3 * g + 2];
+            for (int r = 0; r < kTkRQ; ++r) {
+                float a0, a1, a2, a3;
+                unpack2(sqdist_pair(QX[r], QY[r], QZ[r], X01, Y01, Z01), a0, a1);
+                unpack2(sqdist_pair(QX[r], QY[r], QZ[r], X23, Y23, Z23), a2, a3);
+                if (fminf(min3(a0, a1, a2), a3) < bd[r][K - 1]) {
                     const int j = base + 4 * g;
-                    topk_insert<K>(bd[r], bi[r], sqdist_scalar(qx, qy, qz, X.x, Y.x, Z.x), j);
-                    topk_insert<K>(bd[r], bi[r], sqdist_scalar(qx, qy, qz, X.y, Y.y, Z.y), j + 1);
-                    topk_insert<K>(bd[r], bi[r], sqdist_scalar(qx, qy, qz, X.z, Y.z, Z.z), j + 2);
-                    topk_insert<K>(bd[r], bi[r], sqdist_scalar(qx, qy, qz, X.w, Y.w, Z.w), j + 3);
+                    topk_insert<K>(bd[r], bi[r], a0, j);
+                    topk_insert<K>(bd[r], bi[r], a1, j + 1);
+                    topk_insert<K>(bd[r], bi[r], a2, j + 2);
+                    topk_insert<K>(bd[r], bi[r], a3, j + 3);
                 }
             }
         }

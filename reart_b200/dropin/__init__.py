@@ -108,7 +108,7 @@ def _knn_points_backward(p1, p2, lengths1, lengths2, idx, grad_dists):
 def _furthest_point_sampling_wrapper(B, N, npoint, xyz, temp, out):
     """pointnet2_cuda.furthest_point_sampling_wrapper (networks/pointnet_lib/pointnet2_utils.py:29)."""
     from ..ops import fps_into
-    fps_into(xyz, int(npoint), out)
+    fps_into(xyz, int(npoint), out, temp=temp if torch.is_tensor(temp) else None)
     return 1
 
 

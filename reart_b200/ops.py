@@ -330,15 +330,19 @@ def knn3_blend(query: torch.Tensor, ref_cat: torch.Tensor, flow_cat: torch.Tenso
 
 # --------------------------------------------------------------------------------------- FPS / ball query (no grad)
 @torch.no_grad()
-def fps_into(xyz: torch.Tensor, npoint: int, out: torch.Tensor) -> torch.Tensor:
-    """xyz [B,N,3] -> out [B,npoint] int32 (written in place), starting at index 0."""
+def fps_into(xyz: torch.Tensor, npoint: int, out: torch.Tensor, temp: "torch.Tensor | None" = None) -> torch.Tensor:
+    """xyz [B,N,3] -> out [B,npoint] int32 (written in place), starting at index 0.  Clouds above 32 768 points keep
+    their running distances in ``temp`` [B,N] float32 (allocated here when not given), as the reference's kernel does."""
     _lib.require_cuda(xyz, out)
     L = _lib.lib()
     xyz = _f32c(xyz)
     B, N, _ = xyz.shape
     assert out.dtype == torch.int32 and out.is_contiguous() and out.shape == (B, npoint)
+    if N > 32768 and (temp is None or temp.dtype != torch.float32 or not temp.is_contiguous() or temp.numel() < B * N):
+        temp = torch.empty(B, N, dtype=torch.float32, device=xyz.device)
     with torch.cuda.device(xyz.device):
-        check(L.reart_fps(ptr(xyz), B, N, int(npoint), ptr(out), stream_ptr()), "reart_fps")
+        check(L.reart_fps_temp(ptr(xyz), B, N, int(npoint), ptr(temp) if N > 32768 else None, ptr(out), stream_ptr()),
+              "reart_fps_temp")
     return out
 
 

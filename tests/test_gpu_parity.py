@@ -484,6 +484,25 @@ def test_fps_vs_oracle_and_pointnet2_dropin():
     assert bool(picked.all())
 
 
+def test_fps_beyond_the_register_kernel_limit():
+    """N > 32 768: running distances in the temp buffer the reference's wrapper passes (no size limit, like
+    sampling_gpu.cu:93-209); the samples equal the oracle's, and the prefix of the cloud gives the register kernel's."""
+    import sys
+    from reart_b200 import dropin, ops
+    rng = np.random.default_rng(18)
+    xyz = (rng.random((2, 40000, 3)) - 0.5).astype(np.float32)
+    want = oracle.fps(xyz, 96)
+    got = ops.fps(cu(xyz), 96)
+    assert np.array_equal(got.cpu().numpy(), want)
+    dropin.install(force=True)
+    out = torch.zeros(2, 96, dtype=torch.int32, device=dev())
+    temp = torch.full((2, 40000), 1e10, device=dev())
+    sys.modules["pointnet2_cuda"].furthest_point_sampling_wrapper(2, 40000, 96, cu(xyz), temp, out)
+    assert np.array_equal(out.cpu().numpy(), want)
+    small = ops.fps(cu(xyz[:, :32768]), 64)                                      # register kernel on the same data
+    assert np.array_equal(small.cpu().numpy(), oracle.fps(np.ascontiguousarray(xyz[:, :32768]), 64))
+
+
 # ----------------------------------------------------------------------------------------- full-size properties
 def test_full_size_properties_cfg3_16k():
     """BASELINE cfg3 size (T=64 would take the oracle minutes; properties are size independent, T=8 here):
