@@ -37,6 +37,8 @@ extern "C" {
 
 REART_API const char* reart_version(void);
 REART_API const char* reart_error_string(int code);
+/* the CUDA runtime error behind the most recent REART_ERR_LAUNCH raised by a kernel launch ("none" if there was none) */
+REART_API const char* reart_last_cuda_error(void);
 
 /* ---------------------------------------------------------------------------------------------
  * K=1 nearest neighbour, D=3.

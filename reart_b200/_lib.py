@@ -21,6 +21,7 @@ _vp = ctypes.c_void_p
 SIGNATURES = {
     "reart_version": (ctypes.c_char_p, []),
     "reart_error_string": (ctypes.c_char_p, [_c_int]),
+    "reart_last_cuda_error": (ctypes.c_char_p, []),
     "reart_knn1_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i64]),
     "reart_knn1_fwd": (_c_int, [_vp, _vp, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp, _c_i64, _vp]),
     "reart_chamfer_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i64]),
@@ -111,7 +112,8 @@ def lib() -> ctypes.CDLL:
 
 def check(code: int, what: str) -> None:
     if code != 0:
-        raise ReartError(f"{what} failed: {lib().reart_error_string(code).decode()} ({code})")
+        extra = f"; CUDA: {lib().reart_last_cuda_error().decode()}" if code == -3 else ""
+        raise ReartError(f"{what} failed: {lib().reart_error_string(code).decode()} ({code}){extra}")
 
 
 def ptr(t):

@@ -44,6 +44,11 @@ extern "C" {
 
 const char* reart_version(void) { return "reart_b200 0.1.0 (sm_100a)"; }
 
+const char* reart_last_cuda_error(void) {
+    const int e = reart::last_cuda_error();
+    return e ? cudaGetErrorString((cudaError_t)e) : "none";
+}
+
 const char* reart_error_string(int code) {
     switch (code) {
         case REART_OK: return "ok";
@@ -128,6 +133,7 @@ int reart_chamfer_bidir_fwd(const float* src, const float* tgt, int64_t B, int64
     SymParams sp = {};
     sp.a = src; sp.b_packed = ptgt; sp.keys_a = kf; sp.keys_b = kb;
     sp.B = (int)B; sp.na = (int)N; sp.nb = (int)M; sp.nb_pad = (int)padded_points(M);
+    sp.keys_one_allocation = 1;
     rc = launch_chamfer_sym(sp, stream);
     if (rc) return rc;
     if (sp.col_chunk_pts != 256) return REART_ERR_UNSUPPORTED;
@@ -286,6 +292,7 @@ int reart_skinned_chamfer_fwd_bwd_culled(const float* cano, const float* W, cons
     sp.a = skinned; sp.b_packed = tgt_packed; sp.keys_a = ka; sp.keys_b = kb;
     sp.B = (int)T; sp.na = (int)N; sp.nb = (int)M; sp.nb_pad = (int)padded_points(M);
     sp.col_bound = col_bound;
+    sp.keys_one_allocation = 1;
     if (cull) {
         // seeds = the arg-mins of the previous evaluation (nn_* = -1: none, brute force); bounds, then the culled search
         CullParams cp = {};

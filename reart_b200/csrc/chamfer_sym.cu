@@ -297,7 +297,9 @@ static int launch_sym_rs(SymParams& p, cudaStream_t stream) {
     const size_t bytes_a = sizeof(u64) * (size_t)p.B * p.na, bytes_b = sizeof(u64) * (size_t)p.B * p.nb;
     const char* a0 = reinterpret_cast<const char*>(p.keys_a);
     const char* b0 = reinterpret_cast<const char*>(p.keys_b);
-    if (need_a && need_b && b0 >= a0 + bytes_a && (size_t)(b0 - a0) <= bytes_a + 4096) {
+    // (one memset may only span the gap between the two arrays when both live in ONE allocation of ours -- the fused
+    // pipelines of capi.cu say so with keys_one_allocation; caller-owned arrays may have a stranger's tensor in between)
+    if (p.keys_one_allocation && need_a && need_b && b0 >= a0 + bytes_a && (size_t)(b0 - a0) <= bytes_a + 4096) {
         if (cudaMemsetAsync(p.keys_a, 0xff, (size_t)(b0 - a0) + bytes_b, stream) != cudaSuccess) return kErrLaunch;
     } else {
         if (need_a && cudaMemsetAsync(p.keys_a, 0xff, bytes_a, stream) != cudaSuccess) return kErrLaunch;

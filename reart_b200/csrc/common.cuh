@@ -19,10 +19,19 @@ enum : int {
     kErrUnsupported = -4,
 };
 
+// the CUDA error behind the most recent kErrLaunch (reart_last_cuda_error() reports it)
+inline int& last_cuda_error() {
+    static int e = 0;
+    return e;
+}
+
 #define REART_CHECK_LAUNCH()                                   \
     do {                                                       \
         cudaError_t e__ = cudaGetLastError();                  \
-        if (e__ != cudaSuccess) return reart::kErrLaunch;      \
+        if (e__ != cudaSuccess) {                              \
+            reart::last_cuda_error() = (int)e__;               \
+            return reart::kErrLaunch;                          \
+        }                                                      \
     } while (0)
 
 // ----------------------------------------------------------------------------- packed f32x2

@@ -40,6 +40,7 @@ struct SymParams {
     int qblocks, splits;          // filled by the launcher
     int col_chunk_pts;            // filled by the launcher (32 * R / S)
     int keys_preset;
+    int keys_one_allocation;      // 1: keys_a and keys_b are carved from one workspace (a single memset may span both)
     int variant;                  // 0 = default; 1/2/4/8 = number of column sub-chunks per warp (tuning)
     unsigned* col_bound;          // null, or one word (zero on entry): atomicMax of the finite column minima every CTA
                                   // saw, as float bits -- an upper bound of every final column minimum (energy.cu)
