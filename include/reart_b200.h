@@ -267,6 +267,23 @@ REART_API int reart_knn3_blend(const float* query, const float* ref_cat, const f
                                const int64_t* ref_offsets, int64_t T, int64_t m, float* blended, uint8_t* mask,
                                void* stream);
 
+/* The same blend, bit-identical results, for reference sets that stay fixed over many calls (they do: run_robot.py:78-84
+ * builds pc_ref_list / flow_ref_list once, the loop of :199-202 queries them every iteration).
+ *   reart_flow_refs_sort: once per fit -- sorts every pair's references along x into `sorted`
+ *     (reart_flow_refs_sorted_bytes(total_refs, T) bytes) and writes each pair's start (in 64-byte groups) to
+ *     sorted_offsets [T] int64 (device).  max_refs = the largest per-pair count (host value, <= 16384, else
+ *     REART_ERR_UNSUPPORTED: use reart_knn3_blend).
+ *   reart_knn3_blend_sorted: per call -- buckets the queries by x (query_order [T,m] int32 scratch) and searches only
+ *     the x-slab of references that can still hold one of the 3 nearest (exact: a skipped reference has
+ *     dx*dx > current 3rd best; ties by lowest original index as in reart_knn3_blend). */
+REART_API int64_t reart_flow_refs_sorted_bytes(int64_t total_refs, int64_t T);
+REART_API int reart_flow_refs_sort(const float* ref_cat, const int64_t* ref_offsets, int64_t T, int64_t max_refs,
+                                   void* sorted, int64_t sorted_bytes, int64_t total_refs, int64_t* sorted_offsets,
+                                   void* stream);
+REART_API int reart_knn3_blend_sorted(const float* query, const void* sorted, const int64_t* sorted_offsets,
+                                      const float* flow_cat, const int64_t* ref_offsets, int64_t T, int64_t m,
+                                      int32_t* query_order, float* blended, uint8_t* mask, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Assignment loss (run_robot.py:164-187, run_real.py:180-203, run_sapien.py:179-203; utils/model_utils.py:85-103).
  * reart_lap: for each of B frames the exactly optimal one-to-one matching of n source samples to n target samples

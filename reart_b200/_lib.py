@@ -57,6 +57,9 @@ SIGNATURES = {
     "reart_knn": (_c_int, [_vp, _vp, _c_i64, _c_i64, _c_i64, _c_int, _vp, _vp, _vp]),
     "reart_knn_sq": (_c_int, [_vp, _vp, _c_i64, _c_i64, _c_i64, _c_int, _vp, _vp, _vp]),
     "reart_knn3_blend": (_c_int, [_vp, _vp, _vp, _vp, _c_i64, _c_i64, _vp, _vp, _vp]),
+    "reart_flow_refs_sorted_bytes": (_c_i64, [_c_i64, _c_i64]),
+    "reart_flow_refs_sort": (_c_int, [_vp, _vp, _c_i64, _c_i64, _vp, _c_i64, _c_i64, _vp, _vp]),
+    "reart_knn3_blend_sorted": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _vp, _vp, _vp, _vp]),
     "reart_fps": (_c_int, [_vp, _c_i64, _c_i64, _c_i64, _vp, _vp]),
     "reart_fps_temp": (_c_int, [_vp, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp]),
     "reart_ball_query": (_c_int, [_vp, _vp, _c_i64, _c_i64, _c_i64, ctypes.c_float, _c_int, _vp, _vp]),

@@ -493,6 +493,33 @@ int reart_knn3_blend(const float* query, const float* ref_cat, const float* flow
                              static_cast<cudaStream_t>(stream_));
 }
 
+int64_t reart_flow_refs_sorted_bytes(int64_t total_refs, int64_t T) {
+    if (total_refs < 0 || T < 0) return 0;
+    return flow_refs_sorted_floats(total_refs, T) * (int64_t)sizeof(float);
+}
+
+int reart_flow_refs_sort(const float* ref_cat, const int64_t* ref_offsets, int64_t T, int64_t max_refs, void* sorted,
+                         int64_t sorted_bytes, int64_t total_refs, int64_t* sorted_offsets, void* stream_) {
+    REART_ENTRY();
+    if (T < 0 || max_refs < 0 || total_refs < 0) return REART_ERR_INVALID_ARG;
+    if (T == 0) return REART_OK;
+    if (!ref_cat || !ref_offsets || !sorted || !sorted_offsets) return REART_ERR_INVALID_ARG;
+    if (sorted_bytes < reart_flow_refs_sorted_bytes(total_refs, T)) return REART_ERR_WORKSPACE;
+    return launch_flow_refs_sort(ref_cat, ref_offsets, T, max_refs, static_cast<float*>(sorted), sorted_offsets,
+                                 static_cast<cudaStream_t>(stream_));
+}
+
+int reart_knn3_blend_sorted(const float* query, const void* sorted, const int64_t* sorted_offsets, const float* flow_cat,
+                            const int64_t* ref_offsets, int64_t T, int64_t m, int32_t* query_order, float* blended,
+                            uint8_t* mask, void* stream_) {
+    REART_ENTRY();
+    if (T < 0 || m < 0 || !fits_int(m)) return REART_ERR_INVALID_ARG;
+    if (T == 0 || m == 0) return REART_OK;
+    if (!query || !sorted || !sorted_offsets || !flow_cat || !ref_offsets || !query_order || !blended) return REART_ERR_INVALID_ARG;
+    return launch_knn3_blend_sorted(query, static_cast<const float*>(sorted), sorted_offsets, flow_cat, ref_offsets, T, m,
+                                    query_order, blended, mask, static_cast<cudaStream_t>(stream_));
+}
+
 int reart_lap(const float* src, const int64_t* src_idx, int64_t src_points, const float* tgt, int64_t B, int64_t n,
               int32_t* col4row, double* total, double* dual_u, int warm_start, void* stream_) {
     REART_ENTRY();

@@ -136,6 +136,13 @@ int launch_energy_bwd(const EnergyParams& p, cudaStream_t stream);
 
 int launch_knn(const float* ref, const float* query, int64_t B, int64_t n, int64_t m, int k, float* dist, int64_t* idx,
                int squared, cudaStream_t stream);
+// windowed exact flow blend over x-sorted reference sets (knnk.cu)
+int64_t flow_refs_sorted_floats(int64_t total_refs, int64_t T);
+int launch_flow_refs_sort(const float* ref_cat, const int64_t* ref_off, int64_t T, int64_t max_refs, float* sorted,
+                          int64_t* sorted_off, cudaStream_t stream);
+int launch_knn3_blend_sorted(const float* query, const float* sorted, const int64_t* sorted_off, const float* flow_cat,
+                             const int64_t* ref_off, int64_t T, int64_t m, int* qperm, float* blended,
+                             unsigned char* mask, cudaStream_t stream);
 int launch_knn3_blend(const float* query, const float* ref_cat, const float* flow_cat, const int64_t* ref_off,
                       int64_t T, int64_t m, float* blended, unsigned char* mask, cudaStream_t stream);
 

@@ -40,6 +40,12 @@ class FlowReference:
             off.append(off[-1] + n)
         self.offsets = torch.tensor(off, dtype=torch.int64, device=dev)
         self.T = len(lens)
+        # the sets never change during a fit: sort them along x once for the windowed exact kernel (worth it when the
+        # sets are large; small ones stay on the brute-force kernel, which needs no per-call query ordering)
+        self.max_refs = max(lens) if lens else 0
+        self.sorted_refs = None
+        if self.ref_cat.is_cuda and 2048 <= self.max_refs <= 16384:
+            self.sorted_refs = ops.flow_refs_sort(self.ref_cat, self.offsets, self.max_refs)
 
     def slice(self, p0: int, p1: int) -> "FlowReference":
         """The pairs [p0, p1) as a view (shared storage; offsets stay relative to the concatenated arrays)."""
@@ -47,10 +53,13 @@ class FlowReference:
         sub.ref_cat, sub.flow_cat = self.ref_cat, self.flow_cat
         sub.offsets = self.offsets[p0:p1 + 1].contiguous()
         sub.T = p1 - p0
+        sub.max_refs = self.max_refs
+        sub.sorted_refs = None if self.sorted_refs is None else (self.sorted_refs[0], self.sorted_refs[1][p0:p1].contiguous())
         return sub
 
 
 def blend_anchor_motion_batched(query_list: torch.Tensor, ref: FlowReference):
     """All T frame pairs of run_robot.py:199-202 in one launch: query [T,m,3] -> (flow [T,m,3], mask [T,m])."""
     assert query_list.shape[0] == ref.T
-    return ops.knn3_blend(query_list, ref.ref_cat, ref.flow_cat, ref.offsets)
+    windowed = ref.sorted_refs is not None and query_list.shape[1] >= 2048
+    return ops.knn3_blend(query_list, ref.ref_cat, ref.flow_cat, ref.offsets, sorted_refs=ref.sorted_refs if windowed else None)

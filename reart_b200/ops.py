@@ -313,8 +313,31 @@ def knn(ref: torch.Tensor, query: torch.Tensor, k: int, squared: bool = False):
 
 
 @torch.no_grad()
-def knn3_blend(query: torch.Tensor, ref_cat: torch.Tensor, flow_cat: torch.Tensor, ref_offsets: torch.Tensor):
-    """All frame pairs of the flow loss at once -> (blended [T,m,3], mask [T,m] bool)."""
+def flow_refs_sort(ref_cat: torch.Tensor, ref_offsets: torch.Tensor, max_refs: int):
+    """Sort every pair's reference set along x once (include/reart_b200.h: reart_flow_refs_sort) ->
+    (sorted uint8 buffer, sorted_offsets [T] int64) for ``knn3_blend(..., sorted_refs=...)``; None when a set is too
+    large for the windowed kernel (max_refs > 16384)."""
+    _lib.require_cuda(ref_cat, ref_offsets)
+    L = _lib.lib()
+    ref_cat = _f32c(ref_cat)
+    ref_offsets = ref_offsets.to(torch.int64).contiguous()
+    T = ref_offsets.numel() - 1
+    if T <= 0 or max_refs > 16384:
+        return None
+    total = int(ref_cat.shape[0])
+    nbytes = L.reart_flow_refs_sorted_bytes(total, T)
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=ref_cat.device)
+    soff = torch.empty(T, dtype=torch.int64, device=ref_cat.device)
+    with torch.cuda.device(ref_cat.device):
+        check(L.reart_flow_refs_sort(ptr(ref_cat), ptr(ref_offsets), T, int(max_refs), ptr(buf), nbytes, total, ptr(soff),
+                                     stream_ptr()), "reart_flow_refs_sort")
+    return buf, soff
+
+
+def knn3_blend(query: torch.Tensor, ref_cat: torch.Tensor, flow_cat: torch.Tensor, ref_offsets: torch.Tensor,
+               sorted_refs=None):
+    """All frame pairs of the flow loss at once -> (blended [T,m,3], mask [T,m] bool).  With ``sorted_refs`` (from
+    ``flow_refs_sort`` of the same reference sets) the windowed exact kernel runs: same bits, a fraction of the pairs."""
     _lib.require_cuda(query, ref_cat, flow_cat, ref_offsets)
     L = _lib.lib()
     query, ref_cat, flow_cat = _f32c(query), _f32c(ref_cat), _f32c(flow_cat)
@@ -323,8 +346,14 @@ def knn3_blend(query: torch.Tensor, ref_cat: torch.Tensor, flow_cat: torch.Tenso
     blended = torch.empty(T, m, 3, dtype=torch.float32, device=query.device)
     mask = torch.empty(T, m, dtype=torch.uint8, device=query.device)
     with torch.cuda.device(query.device):
-        check(L.reart_knn3_blend(ptr(query), ptr(ref_cat), ptr(flow_cat), ptr(ref_offsets), T, m, ptr(blended),
-                                 ptr(mask), stream_ptr()), "reart_knn3_blend")
+        if sorted_refs is not None:
+            buf, soff = sorted_refs
+            order = torch.empty(T, m, dtype=torch.int32, device=query.device)
+            check(L.reart_knn3_blend_sorted(ptr(query), ptr(buf), ptr(soff), ptr(flow_cat), ptr(ref_offsets), T, m, ptr(order),
+                                            ptr(blended), ptr(mask), stream_ptr()), "reart_knn3_blend_sorted")
+        else:
+            check(L.reart_knn3_blend(ptr(query), ptr(ref_cat), ptr(flow_cat), ptr(ref_offsets), T, m, ptr(blended),
+                                     ptr(mask), stream_ptr()), "reart_knn3_blend")
     return blended, mask.bool()
 
 

@@ -969,6 +969,52 @@ def test_register_blocked_topk_and_blend_path_vs_oracle():
         assert (M[t].cpu().numpy() == m_o).mean() > 0.999
 
 
+def test_windowed_flow_blend_is_bit_identical_to_brute_force():
+    """reart_knn3_blend_sorted (x-sorted references, x-bucketed queries, slab walk with strict skips) returns the bits of
+    the brute-force reart_knn3_blend: ragged sets, set sizes that are not multiples of 4 / 512, duplicated references
+    (ties -> lowest original index although candidates arrive in x order), an integer lattice (massive ties, many equal
+    x), queries far outside the references, fewer than 3 references, a sliced FlowReference."""
+    from reart_b200 import ops
+    from reart_b200.flow_utils import FlowReference, blend_anchor_motion_batched
+    rng = np.random.default_rng(91)
+    sizes = [4096, 2501, 3, 513, 2, 5000, 1]
+    refs = [(rng.standard_normal((n, 3)) * np.array([0.5, 0.2, 0.3])).astype(np.float32) for n in sizes]
+    refs[1][1200:1210] = refs[1][100:110]                             # exact duplicates
+    lat = np.stack(np.meshgrid(np.arange(16), np.arange(16), np.arange(16), indexing="ij"), -1).reshape(-1, 3)
+    refs[0] = (lat[rng.permutation(4096)] * 0.0625).astype(np.float32)   # lattice in scrambled order
+    flows = [(rng.standard_normal((n, 3)) * 0.05).astype(np.float32) for n in sizes]
+    T, m = len(sizes), 2600
+    q = (rng.standard_normal((T, m, 3)) * np.array([0.5, 0.2, 0.3])).astype(np.float32)
+    q[0] = (rng.integers(0, 33, (m, 3)) * 0.03125).astype(np.float32)   # half-lattice queries: exact ties everywhere
+    q[5, :50] += 40.0                                                   # far outside the references
+    q[1, 7] = refs[1][105]                                              # zero distance to a duplicated pair
+    queries = cu(q)
+    ref = FlowReference([cu(r) for r in refs], [cu(f) for f in flows])
+    assert ref.sorted_refs is not None
+    B_w, M_w = blend_anchor_motion_batched(queries, ref)                # windowed (m >= 2048, sets sorted)
+    B_b, M_b = ops.knn3_blend(queries, ref.ref_cat, ref.flow_cat, ref.offsets)
+    for t in range(T):
+        if sizes[t] >= 3:
+            assert torch.equal(B_w[t], B_b[t]), t
+            assert torch.equal(M_w[t], M_b[t]), t
+    sub = ref.slice(1, 6)
+    B_s, M_s = blend_anchor_motion_batched(queries[1:6].contiguous(), sub)
+    for t in (1, 3, 5):
+        assert torch.equal(B_s[t - 1], B_b[t]) and torch.equal(M_s[t - 1], M_b[t])
+    # and against the oracle on one pair
+    b_o, m_o = oracle.blend_anchor_motion(q[1], refs[1], flows[1])
+    np.testing.assert_allclose(B_w[1].cpu().numpy(), b_o, rtol=1e-4, atol=1e-7)
+    # a realistic articulated sequence: queries = the previous frame's cloud, references = subsampled next frame
+    from reart_b200.synth import make_sequence, make_flow_reference
+    seq = make_sequence(6, 8192, 6, seed=5)
+    r_l, f_l = make_flow_reference(seq, cano_idx=0, n_ref=4096)
+    ref2 = FlowReference([cu(r) for r in r_l], [cu(f) for f in f_l])
+    q2 = cu(np.concatenate((seq["cano"][None], seq["frames"]), 0)[:-1])
+    B2, M2 = blend_anchor_motion_batched(q2, ref2)
+    B2b, M2b = ops.knn3_blend(q2, ref2.ref_cat, ref2.flow_cat, ref2.offsets)
+    assert torch.equal(B2, B2b) and torch.equal(M2, M2b)
+
+
 def test_knn_points_k_greater_than_one_with_autograd():
     from reart_b200.chamfer import knn_points
     rng = np.random.default_rng(40)
