@@ -273,10 +273,10 @@ __global__ void __launch_bounds__(kWinSortThreads) flow_refs_sort_kernel(const f
 // in y,z too, so the lanes of a warp meet their nearest references in the same groups (their insertions coincide instead
 // of serialising).  The order inside a bucket is arbitrary: the order only decides which queries share a warp, never a result.
 __global__ void __launch_bounds__(kWinSortThreads) knnw_order_queries_kernel(const float* __restrict__ query, int m,
-                                                                             int* __restrict__ qperm, int kWinXBits,
-                                                                             int kWinYZBits) {
+                                                                             int* __restrict__ qperm, int x_bits,
+                                                                             int yz_bits) {
     extern __shared__ int hist[];
-    const int kWinBuckets = 1 << (kWinXBits + 2 * kWinYZBits);
+    const int buckets = 1 << (x_bits + 2 * yz_bits);
     __shared__ float s_lo[3][32], s_hi[3][32];
     __shared__ int s_warp[32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -292,29 +292,29 @@ __global__ void __launch_bounds__(kWinSortThreads) knnw_order_queries_kernel(con
         for (int o = 16; o > 0; o >>= 1) { lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o)); hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o)); }
         if (lane == 0) { s_lo[k][warp] = lo[k]; s_hi[k][warp] = hi[k]; }
     }
-    for (int e = tid; e < kWinBuckets; e += kWinSortThreads) hist[e] = 0;
+    for (int e = tid; e < buckets; e += kWinSortThreads) hist[e] = 0;
     __syncthreads();
     float scale[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         lo[k] = s_lo[k][0]; hi[k] = s_hi[k][0];
         for (int w = 1; w < 32; ++w) { lo[k] = fminf(lo[k], s_lo[k][w]); hi[k] = fmaxf(hi[k], s_hi[k][w]); }
-        const int cells = k == 0 ? (1 << kWinXBits) : (1 << kWinYZBits);
+        const int cells = k == 0 ? (1 << x_bits) : (1 << yz_bits);
         scale[k] = hi[k] > lo[k] ? (float)cells / (hi[k] - lo[k]) : 0.f;
     }
     auto bucket = [&](int i) {
-        const int cx = min((1 << kWinXBits) - 1, max(0, (int)((q[(int64_t)i * 3] - lo[0]) * scale[0])));
-        const int cy = min((1 << kWinYZBits) - 1, max(0, (int)((q[(int64_t)i * 3 + 1] - lo[1]) * scale[1])));
-        const int cz = min((1 << kWinYZBits) - 1, max(0, (int)((q[(int64_t)i * 3 + 2] - lo[2]) * scale[2])));
+        const int cx = min((1 << x_bits) - 1, max(0, (int)((q[(int64_t)i * 3] - lo[0]) * scale[0])));
+        const int cy = min((1 << yz_bits) - 1, max(0, (int)((q[(int64_t)i * 3 + 1] - lo[1]) * scale[1])));
+        const int cz = min((1 << yz_bits) - 1, max(0, (int)((q[(int64_t)i * 3 + 2] - lo[2]) * scale[2])));
         // boustrophedon in y and z: consecutive buckets stay neighbours in space
-        const int yy = (cx & 1) ? (1 << kWinYZBits) - 1 - cy : cy;
-        const int zz = (yy & 1) ? (1 << kWinYZBits) - 1 - cz : cz;
-        return (cx << (2 * kWinYZBits)) | (yy << kWinYZBits) | zz;
+        const int yy = (cx & 1) ? (1 << yz_bits) - 1 - cy : cy;
+        const int zz = (yy & 1) ? (1 << yz_bits) - 1 - cz : cz;
+        return (cx << (2 * yz_bits)) | (yy << yz_bits) | zz;
     };
     for (int i = tid; i < m; i += kWinSortThreads) atomicAdd(&hist[bucket(i)], 1);
     __syncthreads();
-    // exclusive scan of the bucket counts: kWinBuckets / 1024 consecutive buckets per thread
-    const int kPer = kWinBuckets / kWinSortThreads;
+    // exclusive scan of the bucket counts: buckets / 1024 consecutive buckets per thread
+    const int kPer = buckets / kWinSortThreads;
     int tsum = 0;
     for (int k = 0; k < kPer; ++k) tsum += hist[tid * kPer + k];
     int incl = tsum;
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(kWinThreads) knn_window_blend_kernel(const flo
                                                                        const int64_t* __restrict__ ref_off,
                                                                        const int* __restrict__ qperm, int m,
                                                                        float* __restrict__ out_blend,
-                                                                       unsigned char* __restrict__ out_mask, int kWinSubGroups) {
+                                                                       unsigned char* __restrict__ out_mask, int sub_groups) {
     __shared__ __align__(16) float tile[kWinTileGroups * 16];
     __shared__ float s_lo[4], s_hi[4], s_r2[4];
     __shared__ int s_cnt[2][4];
@@ -432,8 +432,8 @@ __global__ void __launch_bounds__(kWinThreads) knn_window_blend_kernel(const flo
             for (int e = tid; e < gcount * 4; e += kWinThreads) dst[e] = src[e];
             __syncthreads();
             const float4* __restrict__ t4 = reinterpret_cast<const float4*>(tile);
-            for (int g0 = 0; g0 < gcount; g0 += kWinSubGroups) {
-                const int g1 = min(gcount, g0 + kWinSubGroups);
+            for (int g0 = 0; g0 < gcount; g0 += sub_groups) {
+                const int g1 = min(gcount, g0 + sub_groups);
                 float mine = bd[0][K - 1];
 #pragma unroll
                 for (int r = 1; r < kWinRQ; ++r) mine = fmaxf(mine, bd[r][K - 1]);
