@@ -62,6 +62,32 @@ def test_ctypes_signatures_match_the_header_prototypes():
         assert kind(ret + " ") == ctype_kind.get(restype, "ptr"), (name, ret)
 
 
+def test_relax_tail_args_struct_matches_the_header_field_for_field():
+    """ctypes mirror of reart_relax_tail_args: same field names in the same order, same C type class, so the layouts agree."""
+    import ctypes
+    from reart_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "reart_b200.h")).read()
+    body = re.search(r"typedef struct reart_relax_tail_args \{(.*?)\} reart_relax_tail_args;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for stmt in body.split(";"):
+        stmt = stmt.strip()
+        if not stmt:
+            continue
+        names = [n.strip() for n in stmt.split(",")]
+        first = names[0]
+        ctype = first[:first.rindex(" ")].strip() if "*" not in first else first[:first.rindex("*") + 1].strip()
+        for n in names:
+            ident = re.search(r"(\w+)$", n).group(1)
+            if "*" in first:
+                fields.append((ident, "ptr"))
+            else:
+                fields.append((ident, ctype))
+    kinds = {ctypes.c_void_p: "ptr", ctypes.c_float: "float", ctypes.c_int32: "int32_t", ctypes.c_int64: "int64_t"}
+    mirror = [(n, kinds[t]) for n, t in _lib.RelaxTailArgs._fields_]
+    assert mirror == fields
+
+
 def test_header_cites_reference_for_every_entry_point():
     src = open(os.path.join(ROOT, "include", "reart_b200.h")).read()
     for name in ("utils/chamfer.py:174", "utils/chamfer.py:206", "networks/model.py:63-69", "networks/loss.py:24-29",
