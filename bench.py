@@ -287,7 +287,7 @@ def kernels_of_one_step(engine):
         return None, {}
 
 
-def make_engine(workload, ctx, dev, use_graph, scaling, extra_losses=True, cull=False):
+def make_engine(workload, ctx, dev, use_graph, scaling, extra_losses=True, cull=False, fuse_producer=False):
     """Synthetic sequence + engine of one named workload.  Returns (engine, host cano, host frames, T_total, N, P, desc)."""
     import numpy as np
     import torch
@@ -320,7 +320,8 @@ def make_engine(workload, ctx, dev, use_graph, scaling, extra_losses=True, cull=
         engine = RelaxationEngine(cano_h.to(dev), frames_h.to(dev), num_parts=P, ctx=ctx, use_graph=use_graph, flow_ref=fr,
                                   cano_idx=0, **kwargs)
     else:
-        engine = RelaxationEngine(cano_h.to(dev), frames_h.to(dev), num_parts=P, ctx=ctx, use_graph=use_graph, cull=cull)
+        engine = RelaxationEngine(cano_h.to(dev), frames_h.to(dev), num_parts=P, ctx=ctx, use_graph=use_graph, cull=cull,
+                                  fuse_producer=fuse_producer)
     return engine, cano_h, frames_h, T_total, N, P, desc
 
 
@@ -447,6 +448,23 @@ def culled_entry(workload, ctx, dev, flush, steps, warmup, scaling, brute_loss, 
                     "bounding-box gap exceeds the upper bounds seeded by the previous step's arg-mins are skipped; search keys "
                     "bit-identical to the brute force on the same clouds (tests/test_cull_gpu.py); the engine reorders both "
                     "clouds into k-d leaves, so float sums associate differently and the losses agree to rounding, not bits"}
+
+
+def fused_producer_entry(workload, ctx, dev, flush, steps, warmup, scaling, default_loss, default_ms):
+    """The workload with the skinning fused into the producer side of the search (RelaxationEngine(fuse_producer=True),
+    reart_skinned_chamfer_fwd_bwd_fused): same bits, one launch less; opt-in because it measures slower."""
+    import torch
+    engine, _, _, T_total, N, P, _ = make_engine(workload, ctx, dev, True, scaling, extra_losses=False, fuse_producer=True)
+    ms, _, loss = time_engine_steps(engine, ctx, steps, warmup, flush)
+    final = float(loss.item())
+    n_ours, _ = kernels_of_one_step(engine)
+    engine.release()
+    del engine
+    torch.cuda.empty_cache()
+    return {"enabled_in_headline": False, "ms_per_step": ms, "ms_per_step_default": default_ms, "our_kernels_per_step": n_ours,
+            "final_loss": final, "final_loss_default": default_loss, "bit_identical_loss": final == default_loss,
+            "what": "skinning fused into the search kernel's prologue (SURVEY N1): every search CTA skins its own 2048 "
+                    "canonical points, the first target split also emits the cloud and its x-sorted copy; no skin launch"}
 
 
 def sweep_entry(workload, ctx, dev, flush, steps, warmup, peak_tf):
@@ -639,6 +657,14 @@ def main():
         except Exception as exc:
             culling = {"error": f"{type(exc).__name__}: {exc}"}
 
+    # ---- and with the skinning fused into the producer side of the search (opt-in, measured beside the default)
+    fused = None
+    if args.workload != "cfg4":
+        try:
+            fused = fused_producer_entry(args.workload, ctx, dev, flush, K, W, args.scaling, final_loss, ms_per_step)
+        except Exception as exc:
+            fused = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ---- sweep over the other BASELINE configs (N=1) / candidate fits (N>1)
     sweep = None
     if not args.no_sweep and args.workload == "cfg3_16k":
@@ -680,7 +706,7 @@ def main():
                                        else "table (profiler unavailable)",
                 "step_kernels": {n[:70]: c for n, c in sorted(step_kernels.items(), key=lambda kv: -kv[1])},
                 "cuda_graph": not args.no_graph,
-                "roofline": roofline, "culling": culling, "cpu_baseline": cpu, "cpu_baseline_reference_python": cpu_py,
+                "roofline": roofline, "culling": culling, "fused_producer": fused, "cpu_baseline": cpu, "cpu_baseline_reference_python": cpu_py,
                 "sustained": sustained, "sweep": sweep}
         print(json.dumps(line), flush=True)
     # teardown: captured graphs reference the NCCL communicator; with more than one rank leave through os._exit after

@@ -147,6 +147,17 @@ REART_API int reart_skinned_chamfer_fwd_bwd_culled(const float* cano, const floa
                                                    float* d_fwd, int64_t* i_fwd, float* d_bwd, int64_t* i_bwd,
                                                    int32_t* nn_rows, int32_t* nn_cols, uint64_t* cull_stats,
                                                    void* workspace, int64_t workspace_bytes, void* stream);
+/* The same energy with the skinning FUSED INTO THE PRODUCER SIDE OF THE SEARCH (the composition networks/model.py:63-69 ->
+ * utils/chamfer.py:78-94 in one kernel): every search CTA skins its own 2048 canonical points in its prologue and the
+ * skinned cloud / x-sorted copy are emitted as by-products, so there is no skinning launch and the cloud is not re-read.
+ * For one-hot weight rows (what F.gumbel_softmax(hard=True) and one_hot give, networks/model.py:44,150): hot [N,2] is the
+ * compact form (part id as int32 bits, weight value) written by reart_relax_head; W [N,P] is still read by the backward.
+ * Results are bit-identical to reart_skinned_chamfer_fwd_bwd.  cano, hot, skinned 16-byte aligned. */
+REART_API int reart_skinned_chamfer_fwd_bwd_fused(const float* cano, const float* hot, const float* W, const float* R,
+                                                  const float* tr, const float* tgt, const float* tgt_packed, int64_t T,
+                                                  int64_t N, int64_t M, int64_t P, float* skinned, double* loss, float* gW,
+                                                  float* gR, float* gtr, float* g_skinned, int compute_grad,
+                                                  void* workspace, int64_t workspace_bytes, void* stream);
 
 
 /* ---------------------------------------------------------------------------------------------
@@ -174,6 +185,8 @@ REART_API int reart_gumbel_st_bwd(const float* ysoft, const float* tau, const fl
  *       + 6D -> R (networks/model.py:60).  cano [N,3]; w0 [H,3], b0 [H], w2 [P,H]; expo [N,P]; tau [1]; d6 [T,P,6]
  *       -> logits [N,P] (optional), W [N,P], ysoft [N,P], R [T,P,3,3].  noise_index [N] (optional): point n uses noise row
  *       noise_index[n] -- for callers that reordered the cloud but want the random decisions of the original order.
+ *       hot [N,2] (optional, 16-byte aligned): every row of W has exactly one non-zero; (its part as int32 bits, its value)
+ *       is written here for reart_skinned_chamfer_fwd_bwd_fused.
  * tail: gumbel backward + seg MLP backward + 6D backward + (frames sharded over `world` ranks: the one-shot
  *       peer-memory all-reduce of reart_allreduce_oneshot, inline) + Adam with torch.optim.Adam semantics
  *       (run_robot.py:146-150, 219-221) on w0/b0/w2 (lr_seg) and d6/tr (lr_pose), all in ONE launch with a fixed
@@ -184,7 +197,7 @@ REART_API int reart_gumbel_st_bwd(const float* ysoft, const float* tau, const fl
  * ------------------------------------------------------------------------------------------- */
 REART_API int reart_relax_head(const float* cano, const float* w0, const float* b0, const float* w2, const float* expo,
                                const int64_t* noise_index, const float* tau, const float* d6, int64_t N, int64_t H, int64_t P, int64_t T,
-                               float* logits, float* W, float* ysoft, float* R, void* stream);
+                               float* logits, float* W, float* ysoft, float* R, float* hot, void* stream);
 typedef struct reart_relax_tail_args {
     const float* cano;
     float* w0; float* b0; float* w2;

@@ -81,7 +81,9 @@ class RelaxTailArgs(ctypes.Structure):
 
 
 SIGNATURES.update({
-    "reart_relax_head": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp, _vp, _vp]),
+    "reart_relax_head": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "reart_skinned_chamfer_fwd_bwd_fused": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _c_i64, _vp, _vp, _vp,
+                                                     _vp, _vp, _vp, _c_int, _vp, _c_i64, _vp]),
     "reart_relax_tail_workspace_bytes": (_c_i64, [_c_i64, _c_i64, _c_i64]),
     "reart_relax_tail_ticket_words": (_c_i64, [_c_i64]),
     "reart_relax_tail": (_c_int, [ctypes.POINTER(RelaxTailArgs), _vp]),

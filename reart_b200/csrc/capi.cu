@@ -251,6 +251,12 @@ int reart_skinned_chamfer_fwd_bwd_ex(const float* cano, const float* W, const fl
                                                 workspace_bytes, stream_);
 }
 
+static int energy_pipeline(const float* cano, const float* W, const float* hot, const float* R, const float* tr,
+                           const float* tgt, const float* tgt_packed, int64_t T, int64_t N, int64_t M, int64_t P,
+                           float* skinned, double* loss, float* gW, float* gR, float* gtr, float* g_skinned, int compute_grad,
+                           float* d_fwd, int64_t* i_fwd, float* d_bwd, int64_t* i_bwd, int32_t* nn_rows, int32_t* nn_cols,
+                           uint64_t* cull_stats, void* workspace, int64_t workspace_bytes, void* stream_);
+
 int reart_skinned_chamfer_fwd_bwd_culled(const float* cano, const float* W, const float* R, const float* tr,
                                          const float* tgt, const float* tgt_packed, int64_t T, int64_t N, int64_t M,
                                          int64_t P, float* skinned, double* loss, float* gW, float* gR, float* gtr,
@@ -258,6 +264,29 @@ int reart_skinned_chamfer_fwd_bwd_culled(const float* cano, const float* W, cons
                                          int64_t* i_bwd, int32_t* nn_rows, int32_t* nn_cols, uint64_t* cull_stats,
                                          void* workspace, int64_t workspace_bytes, void* stream_) {
     REART_ENTRY();
+    return energy_pipeline(cano, W, nullptr, R, tr, tgt, tgt_packed, T, N, M, P, skinned, loss, gW, gR, gtr, g_skinned,
+                           compute_grad, d_fwd, i_fwd, d_bwd, i_bwd, nn_rows, nn_cols, cull_stats, workspace, workspace_bytes,
+                           stream_);
+}
+
+int reart_skinned_chamfer_fwd_bwd_fused(const float* cano, const float* hot, const float* W, const float* R,
+                                        const float* tr, const float* tgt, const float* tgt_packed, int64_t T, int64_t N,
+                                        int64_t M, int64_t P, float* skinned, double* loss, float* gW, float* gR,
+                                        float* gtr, float* g_skinned, int compute_grad, void* workspace,
+                                        int64_t workspace_bytes, void* stream_) {
+    REART_ENTRY();
+    if (!hot || (reinterpret_cast<uintptr_t>(hot) & 15) || (reinterpret_cast<uintptr_t>(cano) & 15) ||
+        (reinterpret_cast<uintptr_t>(skinned) & 15))
+        return REART_ERR_INVALID_ARG;
+    return energy_pipeline(cano, W, hot, R, tr, tgt, tgt_packed, T, N, M, P, skinned, loss, gW, gR, gtr, g_skinned, compute_grad,
+                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes, stream_);
+}
+
+static int energy_pipeline(const float* cano, const float* W, const float* hot, const float* R, const float* tr,
+                           const float* tgt, const float* tgt_packed, int64_t T, int64_t N, int64_t M, int64_t P,
+                           float* skinned, double* loss, float* gW, float* gR, float* gtr, float* g_skinned, int compute_grad,
+                           float* d_fwd, int64_t* i_fwd, float* d_bwd, int64_t* i_bwd, int32_t* nn_rows, int32_t* nn_cols,
+                           uint64_t* cull_stats, void* workspace, int64_t workspace_bytes, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (T <= 0 || N <= 0 || M <= 0 || P <= 0 || P > 32 || !fits_int(T) || !fits_int(padded_points(N)) ||
         !fits_int(padded_points(M)))
@@ -286,13 +315,21 @@ int reart_skinned_chamfer_fwd_bwd_culled(const float* cano, const float* W, cons
     unsigned* ticket = reinterpret_cast<unsigned*>(zero + T * N * 24);
     unsigned* col_bound = ticket + 1;
     if (cudaMemsetAsync(zero, 0, (size_t)zero_bytes, stream) != cudaSuccess) return REART_ERR_LAUNCH;
-    int rc = launch_skin_fwd_sorted(cano, W, R, tr, T, N, P, skinned, psrc, perm, xq, n_pad_sorted, stream);
-    if (rc) return rc;
+    int rc = kOk;
     SymParams sp = {};
     sp.a = skinned; sp.b_packed = tgt_packed; sp.keys_a = ka; sp.keys_b = kb;
     sp.B = (int)T; sp.na = (int)N; sp.nb = (int)M; sp.nb_pad = (int)padded_points(M);
     sp.col_bound = col_bound;
     sp.keys_one_allocation = 1;
+    if (hot) {
+        // fused producer: the search skins its own rows and emits the cloud + x-sorted copy as by-products (no skin launch)
+        if (cull) return REART_ERR_INVALID_ARG;
+        sp.sk_cano = cano; sp.sk_hot = hot; sp.sk_R = R; sp.sk_tr = tr; sp.sk_P = (int)P; sp.sk_npad = (int)n_pad_sorted;
+        sp.sk_out = skinned; sp.sk_sorted = psrc; sp.sk_perm = perm; sp.sk_xq = xq;
+    } else {
+        rc = launch_skin_fwd_sorted(cano, W, R, tr, T, N, P, skinned, psrc, perm, xq, n_pad_sorted, stream);
+        if (rc) return rc;
+    }
     if (cull) {
         // seeds = the arg-mins of the previous evaluation (nn_* = -1: none, brute force); bounds, then the culled search
         CullParams cp = {};
@@ -365,12 +402,13 @@ int reart_gumbel_st_bwd(const float* ysoft, const float* tau, const float* gW, i
 
 int reart_relax_head(const float* cano, const float* w0, const float* b0, const float* w2, const float* expo,
                      const int64_t* noise_index, const float* tau, const float* d6, int64_t N, int64_t H, int64_t P, int64_t T, float* logits,
-                     float* W, float* ysoft, float* R, void* stream_) {
+                     float* W, float* ysoft, float* R, float* hot, void* stream_) {
     REART_ENTRY();
     if (N < 0 || T < 0 || H <= 0 || P <= 0 || !fits_int(4 * N) || !fits_int(T * P)) return REART_ERR_INVALID_ARG;
+    if (hot && (reinterpret_cast<uintptr_t>(hot) & 15)) return REART_ERR_INVALID_ARG;
     if (N > 0 && (!cano || !w0 || !b0 || !w2 || !expo || !tau || !W || !ysoft)) return REART_ERR_INVALID_ARG;
     if (T > 0 && (!d6 || !R)) return REART_ERR_INVALID_ARG;
-    return launch_relax_head(cano, w0, b0, w2, expo, noise_index, tau, d6, N, H, P, T, logits, W, ysoft, R,
+    return launch_relax_head(cano, w0, b0, w2, expo, noise_index, tau, d6, N, H, P, T, logits, W, ysoft, R, hot,
                              static_cast<cudaStream_t>(stream_));
 }
 

@@ -51,9 +51,17 @@ struct SymCfg {
 // bounds cannot contain a minimum or a tie of either side and is skipped.  Keys are bit-identical to the brute force.
 constexpr int kBoxFloats = 8;                                  // lo.xyz, hi.xyz, column bound, pad  (32 B per chunk)
 
-template <int R, int S, bool CULL>
+// SKIN = true is the fused PRODUCER (the north-star design): the A rows are not read from memory, every CTA
+// skins its 2048 canonical points itself in the prologue -- one-hot weights in compact form (part, value), the frame's
+// P transforms staged in shared memory -- with the pinned arithmetic of skin.cu (common.cuh skin_axis), so the rows are
+// bit-identical to what skin_fwd_sorted_kernel writes.  The CTAs of the first target split also emit what the later
+// passes read: the AoS skinned cloud, and per warp the x-sorted copy of its 256 rows with perm and the quantile index
+// (a warp-level bitonic sort, no barrier).  This removes the skin launch and the re-read of the skinned cloud.
+template <int R, int S, bool CULL, bool SKIN>
 __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymParams p) {
     using C = SymCfg<R, S>;
+    static_assert(!SKIN || (R == 8 && S == 1 && !CULL), "the fused producer is built for the production configuration");
+    __shared__ float s_tf[SKIN ? 32 * 12 : 1];                // SKIN: [P][12] transforms of this frame
     constexpr int RS = R / S;                                  // points per lane per sub-chunk
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // [stages][tile bytes] | [2][warps][S][tile points] u32 | CULL: [stages][tile chunks][8] f32 boxes
@@ -110,6 +118,86 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymPa
     float best[R], prev[R];
     unsigned bch[R];
     float rlx = INFINITY, rly = INFINITY, rlz = INFINITY, rhx = -INFINITY, rhy = -INFINITY, rhz = -INFINITY;
+    if (SKIN) {
+        // ---- fused producer: skin this thread's 8 consecutive canonical points
+        for (int e = tid; e < p.sk_P * 12; e += kSymThreads) {
+            const int pp = e / 12, k = e - pp * 12;
+            const int64_t tpi = (int64_t)b * p.sk_P + pp;
+            s_tf[e] = k < 9 ? p.sk_R[tpi * 9 + k] : p.sk_tr[tpi * 3 + (k - 9)];
+        }
+        __syncthreads();
+        const int i0 = qbase + warp * 256 + lane * 8;
+        float cf[24];
+        int2 hot[8];
+        if (i0 + 8 <= p.na) {                                  // 96 B of cano and 64 B of (part, value) per lane: vector loads
+            const float4* c4 = reinterpret_cast<const float4*>(p.sk_cano + (int64_t)i0 * 3);
+            const int4* h4 = reinterpret_cast<const int4*>(p.sk_hot + (int64_t)i0 * 2);
+#pragma unroll
+            for (int v = 0; v < 6; ++v) { const float4 t = __ldg(c4 + v); cf[4 * v] = t.x; cf[4 * v + 1] = t.y; cf[4 * v + 2] = t.z; cf[4 * v + 3] = t.w; }
+#pragma unroll
+            for (int v = 0; v < 4; ++v) { const int4 t = __ldg(h4 + v); hot[2 * v] = make_int2(t.x, t.y); hot[2 * v + 1] = make_int2(t.z, t.w); }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int i = min(i0 + r, p.na - 1);
+                cf[3 * r] = p.sk_cano[3 * (int64_t)i]; cf[3 * r + 1] = p.sk_cano[3 * (int64_t)i + 1]; cf[3 * r + 2] = p.sk_cano[3 * (int64_t)i + 2];
+                hot[r] = make_int2(__float_as_int(p.sk_hot[2 * (int64_t)i]), __float_as_int(p.sk_hot[2 * (int64_t)i + 1]));
+            }
+        }
+        float xr[8], yr[8], zr[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            xr[r] = yr[r] = zr[r] = INFINITY;                  // out-of-range rows never win a column and sort last
+            if (i0 + r < p.na) {
+                const float* m = s_tf + min(max(hot[r].x, 0), p.sk_P - 1) * 12;
+                const float wv = __int_as_float(hot[r].y);
+                const float cx = cf[3 * r], cy = cf[3 * r + 1], cz = cf[3 * r + 2];
+                // skin.cu: acc = 0; acc = fma(w, R_row . c + t, acc) for the one non-zero weight
+                xr[r] = __fmaf_rn(wv, skin_axis(cx, cy, cz, m[0], m[1], m[2], m[9]), 0.f);
+                yr[r] = __fmaf_rn(wv, skin_axis(cx, cy, cz, m[3], m[4], m[5], m[10]), 0.f);
+                zr[r] = __fmaf_rn(wv, skin_axis(cx, cy, cz, m[6], m[7], m[8], m[11]), 0.f);
+            }
+            QX[r] = pack2(xr[r], xr[r]); QY[r] = pack2(yr[r], yr[r]); QZ[r] = pack2(zr[r], zr[r]);
+            best[r] = INFINITY; prev[r] = INFINITY; bch[r] = 0u;
+        }
+        const int blk = qbase / 256 + warp;                    // the 256-point block this warp owns
+        const int nblk = p.sk_npad / 256;
+        if (split == 0 && blk < nblk) {
+            // ---- by-products, written once per (frame, row block): AoS cloud, x-sorted block, perm, quantile index
+            float* out = p.sk_out + ((int64_t)b * p.na + i0) * 3;
+            if (i0 + 8 <= p.na && (p.na & 3) == 0) {
+                float4* o4 = reinterpret_cast<float4*>(out);
+                o4[0] = make_float4(xr[0], yr[0], zr[0], xr[1]); o4[1] = make_float4(yr[1], zr[1], xr[2], yr[2]);
+                o4[2] = make_float4(zr[2], xr[3], yr[3], zr[3]); o4[3] = make_float4(xr[4], yr[4], zr[4], xr[5]);
+                o4[4] = make_float4(yr[5], zr[5], xr[6], yr[6]); o4[5] = make_float4(zr[6], xr[7], yr[7], zr[7]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (i0 + r < p.na) { out[3 * r] = xr[r]; out[3 * r + 1] = yr[r]; out[3 * r + 2] = zr[r]; }
+            }
+            float* stg = reinterpret_cast<float*>(colmin) + warp * 768;      // the column buffers are idle until the main loop
+            u64 key[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int e = lane * 8 + r;
+                stg[e] = xr[r]; stg[256 + e] = yr[r]; stg[512 + e] = zr[r];
+                key[r] = ((u64)orderable_bits(xr[r]) << 32) | (u64)e;
+            }
+            __syncwarp();
+            warp_bitonic_sort256(key, lane);
+            float* sorted_b = p.sk_sorted + (int64_t)b * p.sk_npad * 3;
+            unsigned long long pm = 0ull;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int src = (int)(key[r] & 0xffu), pos = lane * 8 + r;
+                const float sx = stg[src];
+                sorted_block_store(sorted_b, blk, pos, sx, stg[256 + src], stg[512 + src]);
+                pm |= (unsigned long long)src << (8 * r);
+                if (r == 7 && (lane & 1)) p.sk_xq[((int64_t)b * nblk + blk) * kQuantiles + (pos >> 4)] = sx;
+            }
+            *reinterpret_cast<unsigned long long*>(p.sk_perm + (int64_t)b * p.sk_npad + (int64_t)blk * 256 + lane * 8) = pm;
+        }
+    } else {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int i = qbase + warp * (32 * R) + (r / RS) * (32 * RS) + lane * RS + (r % RS);
@@ -123,6 +211,7 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_kernel(const SymPa
         }
         QX[r] = pack2(x, x); QY[r] = pack2(y, y); QZ[r] = pack2(z, z);
         best[r] = INFINITY; prev[r] = INFINITY; bch[r] = 0u;
+    }
     }
     float rbound = INFINITY;                                   // upper bound of the final minima of this warp's rows
     unsigned evaluated = 0u;
@@ -281,7 +370,7 @@ static int sym_choose_splits(int64_t B, int qblocks, int chunks_total, int tile_
     return best_s;
 }
 
-template <int R, int S, bool CULL>
+template <int R, int S, bool CULL, bool SKIN = false>
 static int launch_sym_rs(SymParams& p, cudaStream_t stream) {
     using C = SymCfg<R, S>;
     p.qblocks = (int)ceil_div(p.na, R * kSymThreads);
@@ -310,13 +399,13 @@ static int launch_sym_rs(SymParams& p, cudaStream_t stream) {
     int devid = 0;
     cudaGetDevice(&devid);
     if (devid < 0 || devid >= 64 || !attr_done[devid]) {
-        if (cudaFuncSetAttribute(chamfer_sym_kernel<R, S, CULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(chamfer_sym_kernel<R, S, CULL, SKIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(C::kSmem + kSymStages * C::kTileChunks * kBoxFloats * 4)) != cudaSuccess)
             return kErrLaunch;
         if (devid >= 0 && devid < 64) attr_done[devid] = true;
     }
     const size_t smem = C::kSmem + (CULL ? (size_t)kSymStages * C::kTileChunks * kBoxFloats * 4 : 0);
-    chamfer_sym_kernel<R, S, CULL><<<(unsigned)items, kSymThreads, smem, stream>>>(p);
+    chamfer_sym_kernel<R, S, CULL, SKIN><<<(unsigned)items, kSymThreads, smem, stream>>>(p);
     REART_CHECK_LAUNCH();
     return kOk;
 }
@@ -325,6 +414,12 @@ int launch_chamfer_sym(SymParams& p, cudaStream_t stream) {
     // Measured on B200 (profiles/r01_sym_variants.log, T=64 x 16k): S=1 3.70 ms, S=2 3.87, S=4 4.17, S=8 4.45 --
     // one REDUX per target (S=1, 256-point column chunks) is the fastest search even after paying for the wider
     // index recovery (which the x-sorted packed copy makes cheap, skin.cu / energy.cu).
+    if (p.sk_cano) {                                           // fused producer (one-hot weights in compact form)
+        if (p.cull || !p.sk_hot || !p.sk_R || !p.sk_tr || !p.sk_out || !p.sk_sorted || !p.sk_perm || !p.sk_xq ||
+            p.sk_P <= 0 || p.sk_P > 32 || p.sk_npad % 256 != 0 || p.sk_npad < p.na)
+            return kErrInvalidArg;
+        return launch_sym_rs<8, 1, false, true>(p, stream);
+    }
     if (p.cull) {
         if (!p.colbox || !p.rowbound) return kErrInvalidArg;
         p.row_chunks = (int)ceil_div(p.na, 256);

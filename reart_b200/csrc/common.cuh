@@ -260,6 +260,45 @@ __device__ __forceinline__ int rescan_sorted_chunk_q(const float* __restrict__ s
     return base + (best == 0x7fffffff ? 0 : best);
 }
 
+// One axis of a skinned point, R_row . c + t, with the operation order pinned: every kernel that skins (skin.cu, and the
+// producer side of chamfer_sym.cu) must give the same bits, because the search holds its rows in registers while the
+// energy passes re-read them from memory.  (This is the contraction nvcc chose for the plain expression in round 1.)
+__device__ __forceinline__ float skin_axis(float cx, float cy, float cz, float m0, float m1, float m2, float t) {
+    return __fadd_rn(__fmaf_rn(cz, m2, __fmaf_rn(cx, m0, __fmul_rn(cy, m1))), t);
+}
+
+// Bitonic sort of 256 keys held by ONE warp, 8 per lane (key index e = 8 * lane + r), ascending in e.  Exchange distances
+// below 8 are register swaps inside a lane, the others one 64-bit shuffle per key; no shared memory, no barrier.
+__device__ __forceinline__ void warp_bitonic_sort256(u64 (&key)[8], int lane) {
+#pragma unroll
+    for (int k = 2; k <= 256; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 8) {
+                const bool lower = (lane & (j >> 3)) == 0;                          // (e & j) == 0
+                const bool asc = k >= 256 ? true : ((lane & (k >> 3)) == 0);        // (e & k) == 0
+                const bool keep_min = lower == asc;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const u64 other = __shfl_xor_sync(0xffffffffu, key[r], j >> 3);
+                    key[r] = keep_min ? (other < key[r] ? other : key[r]) : (other > key[r] ? other : key[r]);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    if ((r & j) == 0) {                                             // pair (r, r | j), r the lower index
+                        const bool asc = k >= 8 ? (k >= 256 ? true : ((lane & (k >> 3)) == 0)) : ((r & k) == 0);
+                        const u64 a = key[r], c = key[r | j];
+                        const u64 lo = a < c ? a : c, hi = a < c ? c : a;
+                        key[r] = asc ? lo : hi;
+                        key[r | j] = asc ? hi : lo;
+                    }
+                }
+            }
+        }
+    }
+}
+
 // Writes one point of a sorted block (used by the two kernels that build the copy).
 __device__ __forceinline__ void sorted_block_store(float* __restrict__ sorted_b, int64_t chunk, int k, float x, float y, float z) {
     float* blk = sorted_b + chunk * kSortedChunkFloats;

@@ -50,6 +50,16 @@ struct SymParams {
     const float* rowbound;        // [B, ceil(na/256)]: upper bound of the final minima of each 256-row chunk
     int row_chunks;               // filled by the launcher
     unsigned long long* cull_stats;   // null, or [2] (zero on entry): (warp, chunk) pairs evaluated / offered
+    // fused producer (chamfer_sym.cu SKIN = true): sk_cano != null -> `a` is not read, the rows are skinned in the kernel
+    const float* sk_cano;         // [na,3] canonical cloud
+    const float* sk_hot;          // [na,2] one-hot weights in compact form: (part as int bits, weight value)
+    const float* sk_R;            // [B,P,9]
+    const float* sk_tr;           // [B,P,3]
+    int sk_P, sk_npad;            // parts; padded points of the sorted copy (multiple of 256)
+    float* sk_out;                // out [B,na,3] skinned cloud (AoS)
+    float* sk_sorted;             // out [B,sk_npad*3] x-sorted blocks (common.cuh layout)
+    unsigned char* sk_perm;       // out [B,sk_npad]
+    float* sk_xq;                 // out [B,sk_npad/256,16]
 };
 struct CullParams {
     const float* a;               // [B,na,3] rows (skinned cloud)
@@ -166,7 +176,7 @@ int launch_assign_loss_grad(const float* skinned, const int64_t* src_idx, const 
 // Fused frame-independent head / tail of one relaxation iteration (relax.cu).
 int launch_relax_head(const float* cano, const float* w0, const float* b0, const float* w2, const float* expo,
                       const int64_t* noise_index, const float* tau, const float* d6, int64_t N, int64_t H, int64_t P, int64_t T, float* logits,
-                      float* W, float* ysoft, float* R, cudaStream_t stream);
+                      float* W, float* ysoft, float* R, float* hot, cudaStream_t stream);
 struct RelaxTail {
     const float* cano;            // [N,3]
     float* w0; float* b0; float* w2;              // seg MLP parameters [H,3], [H], [P,H] -- updated in place

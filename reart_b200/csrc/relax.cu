@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(kHeadThreads) relax_head_kernel(const float* _
                                                                   const float* __restrict__ d6, int N, int H, int P,
                                                                   int TP, int point_blocks, float* __restrict__ logits,
                                                                   float* __restrict__ W, float* __restrict__ ysoft,
-                                                                  float* __restrict__ R) {
+                                                                  float* __restrict__ R, float* __restrict__ hot_out) {
     if ((int)blockIdx.x >= point_blocks) {                    // trailing blocks: 6D -> R, one thread per (frame, part)
         const int i = ((int)blockIdx.x - point_blocks) * kHeadThreads + threadIdx.x;
         if (i < TP) {
@@ -104,14 +104,17 @@ __global__ void __launch_bounds__(kHeadThreads) relax_head_kernel(const float* _
             const float y = z[p];
             if (logits) logits[(int64_t)n * P + p] = acc[p];
             ysoft[(int64_t)n * P + p] = y;
-            W[(int64_t)n * P + p] = ((p == hot ? 1.0f : 0.0f) - y) + y;
+            const float wv = ((p == hot ? 1.0f : 0.0f) - y) + y;
+            W[(int64_t)n * P + p] = wv;
+            // the row's ONE non-zero in compact form for the fused producer of the search (every other entry is (0 - y) + y = 0)
+            if (hot_out && p == hot) reinterpret_cast<int2*>(hot_out)[n] = make_int2(hot, __float_as_int(wv));
         }
     }
 }
 
 int launch_relax_head(const float* cano, const float* w0, const float* b0, const float* w2, const float* expo,
                       const int64_t* noise_index, const float* tau, const float* d6, int64_t N, int64_t H, int64_t P, int64_t T, float* logits,
-                      float* W, float* ysoft, float* R, cudaStream_t stream) {
+                      float* W, float* ysoft, float* R, float* hot, cudaStream_t stream) {
     if (N <= 0 && T <= 0) return kOk;
     if (H <= 0 || H > 1024 || P <= 0 || P > 32) return kErrUnsupported;
     const int point_blocks = (int)ceil_div(kMlpLanes * N, kHeadThreads);
@@ -121,7 +124,7 @@ int launch_relax_head(const float* cano, const float* w0, const float* b0, const
         const size_t smem = (size_t)H * (4 + PM + 4) * sizeof(float);                                                \
         if (smem > 48 * 1024) return kErrUnsupported;                                                                \
         relax_head_kernel<PM><<<(unsigned)(point_blocks + pose_blocks), kHeadThreads, smem, stream>>>(               \
-            cano, w0, b0, w2, expo, noise_index, tau, d6, (int)N, (int)H, (int)P, (int)(T * P), point_blocks, logits, W, ysoft, R); \
+            cano, w0, b0, w2, expo, noise_index, tau, d6, (int)N, (int)H, (int)P, (int)(T * P), point_blocks, logits, W, ysoft, R, hot); \
     } while (0)
     if (P <= 8) REART_HEAD(8);
     else if (P <= 16) REART_HEAD(16);

@@ -48,10 +48,10 @@ __global__ void __launch_bounds__(kSkinThreads) skin_fwd_kernel(const float* __r
                 const float wp = __ldg(w + p);
                 if (wp != 0.f) {
                     const float* m = tf + p * 12;
-                    const float vx = cx * m[0] + cy * m[1] + cz * m[2] + m[9];
-                    const float vy = cx * m[3] + cy * m[4] + cz * m[5] + m[10];
-                    const float vz = cx * m[6] + cy * m[7] + cz * m[8] + m[11];
-                    ax += wp * vx; ay += wp * vy; az += wp * vz;
+                    // pinned operation order (common.cuh skin_axis): the fused producer of chamfer_sym.cu must give these bits
+                    ax = __fmaf_rn(wp, skin_axis(cx, cy, cz, m[0], m[1], m[2], m[9]), ax);
+                    ay = __fmaf_rn(wp, skin_axis(cx, cy, cz, m[3], m[4], m[5], m[10]), ay);
+                    az = __fmaf_rn(wp, skin_axis(cx, cy, cz, m[6], m[7], m[8], m[11]), az);
                 }
             }
             float* o = out + ((int64_t)(t0 + f) * N + n) * 3;
@@ -128,10 +128,10 @@ __global__ void __launch_bounds__(kSortBlock) skin_fwd_sorted_kernel(const float
                 const float wp = __ldg(w + p);
                 if (wp != 0.f) {
                     const float* m = tf + p * 12;
-                    const float vx = cx * m[0] + cy * m[1] + cz * m[2] + m[9];
-                    const float vy = cx * m[3] + cy * m[4] + cz * m[5] + m[10];
-                    const float vz = cx * m[6] + cy * m[7] + cz * m[8] + m[11];
-                    ax += wp * vx; ay += wp * vy; az += wp * vz;
+                    // pinned operation order (common.cuh skin_axis): the fused producer of chamfer_sym.cu must give these bits
+                    ax = __fmaf_rn(wp, skin_axis(cx, cy, cz, m[0], m[1], m[2], m[9]), ax);
+                    ay = __fmaf_rn(wp, skin_axis(cx, cy, cz, m[3], m[4], m[5], m[10]), ay);
+                    az = __fmaf_rn(wp, skin_axis(cx, cy, cz, m[6], m[7], m[8], m[11]), az);
                 }
             }
             float* o = out + ((int64_t)(t0 + f) * N + n) * 3;

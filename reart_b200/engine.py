@@ -150,7 +150,7 @@ class RelaxationEngine(_EngineBase):
                  trans_lr: float = 1e-2, seg_lr: float = 1e-3, weight_decay: float = 0.0, use_graph: bool = True,
                  seed: int = 2, flow_ref=None, cano_idx: int = 0, lambda_flow: float = 1.0, robust_flow: bool = False,
                  native: Optional[bool] = None, betas=(0.9, 0.999), eps: float = 1e-8, assign: Optional[dict] = None,
-                 cull: Optional[bool] = None):
+                 cull: Optional[bool] = None, fuse_producer: bool = False):
         """assign: optional dict(downsample=4, assign_gap=5, lambda_assign=0.3, assign_iter=0, mode="add"|"replace")
         enabling the assignment loss (run_robot.py:164-187): from iteration ``assign_iter`` on it is ADDED to the Chamfer
         loss (run_real.py / run_sapien.py) or REPLACES it (run_robot.py's if/else); assignments are refreshed
@@ -177,6 +177,9 @@ class RelaxationEngine(_EngineBase):
         # ``perm_cano`` / ``perm_frames`` map engine order -> caller order (engine.skinned[:, k] is caller point perm_cano[k]).
         # The brute-force search stays the default: it is the kernel the roofline is quoted on and the order-preserving path.
         self.cull = bool(cull) if cull is not None else False
+        # fuse_producer: skin inside the search kernel's prologue (reart_skinned_chamfer_fwd_bwd_fused).  Bit-identical,
+        # one launch less, but measured SLOWER than the separate skin kernel on B200 (profiles/r02_fused_producer.md), so opt-in.
+        self.fuse_producer = bool(fuse_producer) and not self.cull
         if self.cull and (flow_ref is not None or native is False):
             raise ValueError("exact tile culling runs on the native fused iteration (recon / assignment losses)")
         self.perm_cano = self.perm_frames = None
@@ -244,6 +247,7 @@ class RelaxationEngine(_EngineBase):
         b = self._nat = {}
         b["expo"] = torch.empty(N, P, **f32)
         b["W"], b["ysoft"] = torch.empty(N, P, **f32), torch.empty(N, P, **f32)
+        b["hot"] = torch.empty(N, 2, **f32)                      # the one non-zero of every row of W: (part bits, value)
         b["R"] = torch.empty(T, P, 3, 3, **f32)
         b["skinned"] = torch.empty(T, N, 3, **f32)
         b["loss64"] = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -337,11 +341,17 @@ class RelaxationEngine(_EngineBase):
                 ptr(b["skinned"]), ptr(b["loss64"]), ptr(gW), ptr(gR), ptr(gtr), ptr(g_skinned), compute_grad, None, None, None,
                 None, ptr(b["nn_rows"]), ptr(b["nn_cols"]), ptr(b["cull_stats"]), ptr(b["ws"]), b["ws_bytes"], stream_ptr()),
                 "reart_skinned_chamfer_fwd_bwd_culled")
-        else:
+        elif not self.fuse_producer:
             check(L.reart_skinned_chamfer_fwd_bwd(
                 ptr(self.cano), ptr(b["W"]), ptr(b["R"]), ptr(m.proposal_t), ptr(self.frames), ptr(self.frames_packed), T, N, M, P,
                 ptr(b["skinned"]), ptr(b["loss64"]), ptr(gW), ptr(gR), ptr(gtr), ptr(g_skinned), compute_grad, ptr(b["ws"]),
                 b["ws_bytes"], stream_ptr()), "reart_skinned_chamfer_fwd_bwd")
+        else:
+            # skinning fused into the producer side of the search (the weights are one-hot: the head wrote them in compact form)
+            check(L.reart_skinned_chamfer_fwd_bwd_fused(
+                ptr(self.cano), ptr(b["hot"]), ptr(b["W"]), ptr(b["R"]), ptr(m.proposal_t), ptr(self.frames), ptr(self.frames_packed),
+                T, N, M, P, ptr(b["skinned"]), ptr(b["loss64"]), ptr(gW), ptr(gR), ptr(gtr), ptr(g_skinned), compute_grad, ptr(b["ws"]),
+                b["ws_bytes"], stream_ptr()), "reart_skinned_chamfer_fwd_bwd_fused")
 
     def culling_stats(self):
         """(evaluated, offered) (warp, 32-target chunk) pairs since the last call; resets the counters.  Host sync."""
@@ -366,7 +376,7 @@ class RelaxationEngine(_EngineBase):
         with torch.cuda.device(self.cano.device):
             check(L.reart_relax_head(ptr(self.cano), ptr(conv0.weight), ptr(conv0.bias), ptr(conv2.weight), ptr(b["expo"]),
                                      ptr(self.perm_cano), ptr(self.tau), ptr(m.proposal_6d), N, H, P, T, None, ptr(b["W"]), ptr(b["ysoft"]),
-                                     ptr(b["R"]), stream_ptr()), "reart_relax_head")
+                                     ptr(b["R"]), ptr(b["hot"]), stream_ptr()), "reart_relax_head")
             if not use_assign:
                 self._energy_call(L, b, T, N, M, P, b["gW"], b["gR"], b["gtr"], None, 1)
             else:

@@ -637,13 +637,57 @@ def test_relax_head_equals_the_separate_kernels():
     d6 = torch.randn(T, P, 6, device=dev(), generator=g)
     logits, W, ys = (torch.empty(N, P, device=dev()) for _ in range(3))
     R = torch.empty(T, P, 3, 3, device=dev())
+    hot = torch.empty(N, 2, device=dev())
     _lib.check(L.reart_relax_head(_lib.ptr(x), _lib.ptr(w0), _lib.ptr(b0), _lib.ptr(w2), _lib.ptr(expo), None, _lib.ptr(tau), _lib.ptr(d6),
-                                  N, H, P, T, _lib.ptr(logits), _lib.ptr(W), _lib.ptr(ys), _lib.ptr(R), _lib.stream_ptr()), "head")
+                                  N, H, P, T, _lib.ptr(logits), _lib.ptr(W), _lib.ptr(ys), _lib.ptr(R), _lib.ptr(hot), _lib.stream_ptr()), "head")
+    # compact form of the weights: every row has exactly one non-zero, (its part, its value)
+    assert int((W != 0).sum()) == N
+    part = hot.view(torch.int32)[:, 0].long()
+    assert torch.equal(part, (W != 0).float().argmax(dim=1)) and torch.equal(hot[:, 1], W.gather(1, part[:, None])[:, 0])
     lg2 = ops.seg_mlp(x, w0, b0, w2)
     W2, ys2 = torch.empty_like(W), torch.empty_like(ys)
     _lib.check(L.reart_gumbel_st_fwd(_lib.ptr(lg2), _lib.ptr(expo), _lib.ptr(tau), N, P, _lib.ptr(W2), _lib.ptr(ys2), _lib.stream_ptr()), "g")
     assert torch.equal(logits, lg2) and torch.equal(W, W2) and torch.equal(ys, ys2)
     assert torch.equal(R, ops.rot6d(d6))
+
+
+def test_fused_producer_energy_is_bit_identical_to_the_pipelined_one():
+    """reart_skinned_chamfer_fwd_bwd_fused (the search CTAs skin their own rows, cloud + x-sorted copy emitted as
+    by-products, no skin launch) vs reart_skinned_chamfer_fwd_bwd: skinned cloud, loss and all gradients equal bit for bit;
+    N not a multiple of 2048 / 256 / 8 / 4, few and many frames (one and several target splits)."""
+    from reart_b200 import _lib, ops
+    L = _lib.lib()
+    rng = np.random.default_rng(77)
+    for T, N, M, P in ((3, 3001, 2777, 6), (2, 4096, 4096, 15), (9, 2048 + 8, 1500, 20), (1, 777, 900, 3)):
+        seq = synthetic_sequence(T, max(N, M), P, seed=11)
+        cano = cu(seq["cano"][:N]); frames = cu(seq["frames"][:, :M])
+        part = torch.from_numpy(seq["part"][:N].astype(np.int64)).to(dev())
+        val = (1.0 + (torch.rand(N, device=dev()) - 0.5) * 1e-6).float()          # 1 +- ulps, like the straight-through weights
+        W = torch.zeros(N, P, device=dev()); W[torch.arange(N), part] = val
+        hot = torch.empty(N, 2, device=dev()); hot.view(torch.int32)[:, 0] = part.int(); hot[:, 1] = val
+        R = cu(np.ascontiguousarray(seq["pose"][:, :, :3, :3])); tr = cu(np.ascontiguousarray(seq["pose"][:, :, :3, 3]))
+        tr = tr + torch.randn_like(tr) * 0.01
+        packed = ops.pack_cloud(frames)
+        nbytes = int(L.reart_energy_workspace_bytes(T, N, M))
+        outs = []
+        for fused in (False, True):
+            ws = _lib.workspace(nbytes, dev())
+            sk = torch.full((T, N, 3), float("nan"), device=dev()); loss = torch.zeros(1, dtype=torch.float64, device=dev())
+            gW, gR, gtr = torch.empty(N, P, device=dev()), torch.empty(T, P, 9, device=dev()), torch.empty(T, P, 3, device=dev())
+            if fused:
+                _lib.check(L.reart_skinned_chamfer_fwd_bwd_fused(
+                    _lib.ptr(cano), _lib.ptr(hot), _lib.ptr(W), _lib.ptr(R), _lib.ptr(tr), _lib.ptr(frames), _lib.ptr(packed), T, N, M, P,
+                    _lib.ptr(sk), _lib.ptr(loss), _lib.ptr(gW), _lib.ptr(gR), _lib.ptr(gtr), None, 1, _lib.ptr(ws), nbytes,
+                    _lib.stream_ptr()), "fused")
+            else:
+                _lib.check(L.reart_skinned_chamfer_fwd_bwd(
+                    _lib.ptr(cano), _lib.ptr(W), _lib.ptr(R), _lib.ptr(tr), _lib.ptr(frames), _lib.ptr(packed), T, N, M, P,
+                    _lib.ptr(sk), _lib.ptr(loss), _lib.ptr(gW), _lib.ptr(gR), _lib.ptr(gtr), None, 1, _lib.ptr(ws), nbytes,
+                    _lib.stream_ptr()), "pipelined")
+            torch.cuda.synchronize()
+            outs.append((sk, loss, gW, gR, gtr))
+        for a, b in zip(*outs):
+            assert torch.equal(a, b), (T, N, M, P)
 
 
 def test_kinematic_engine_recovers_joint_angles_on_a_synthetic_tree():

@@ -112,8 +112,8 @@ def test_built_library_is_sm100a_sass_with_bulk_tma_and_packed_fp32():
     arch, kernels = sass_summary.census()
     assert arch == ["sm_100a"]
     by = lambda frag: [k for n, k in kernels.items() if frag in n]
-    sym = by("chamfer_sym_kernelILi8ELi1E")                   # brute-force and culled instantiation
-    assert len(sym) == 2
+    sym = by("chamfer_sym_kernelILi8ELi1E")                   # brute-force, culled and fused-producer instantiations
+    assert len(sym) == 3
     for k in sym:
         assert k["UBLKCP"] >= 2 and k["FFMA2"] > 100 and k["FADD2"] > 100 and k["FMNMX3"] > 50 and k["REDUX"] > 10
     assert all(k["UBLKCP"] >= 1 and k["FFMA2"] > 0 for k in by("knn1_main_kernel"))
