@@ -690,6 +690,26 @@ def test_fused_producer_energy_is_bit_identical_to_the_pipelined_one():
             assert torch.equal(a, b), (T, N, M, P)
 
 
+def test_engine_with_fused_producer_follows_the_default_optimisation_bit_for_bit():
+    """RelaxationEngine(fuse_producer=True) -- the head's compact one-hot weights feed the search's skinning prologue --
+    takes exactly the steps of the default engine (skin kernel -> search kernel): every loss equal, final parameters equal,
+    eager and under the CUDA graph."""
+    from reart_b200.engine import RelaxationEngine, tau_schedule
+    seq = synthetic_sequence(5, 3000, 6, seed=4)
+    cano, frames = cu(seq["cano"]), cu(seq["frames"])
+    runs = {}
+    for fused, graph in ((False, False), (True, False), (True, True)):
+        eng = RelaxationEngine(cano, frames, num_parts=6, use_graph=graph, seed=2, fuse_producer=fused)
+        torch.manual_seed(9)
+        losses = [float(eng.step(tau_schedule(i, 100, 5.0, 1.0))) for i in range(12)]
+        runs[(fused, graph)] = (losses, eng.model.proposal_6d.detach().clone(), eng.skinned.clone())
+        eng.release()
+    ref = runs[(False, False)]
+    for key in ((True, False), (True, True)):
+        assert runs[key][0] == ref[0], key
+        assert torch.equal(runs[key][1], ref[1]) and torch.equal(runs[key][2], ref[2]), key
+
+
 def test_kinematic_engine_recovers_joint_angles_on_a_synthetic_tree():
     """--model=kinematic (networks/model.py:73-166): revolute chain with known screws; start from perturbed
     angles and check the fused FK + skin + Chamfer iteration drives the energy down."""
