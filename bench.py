@@ -425,7 +425,7 @@ def sustained_run(engine, ctx, seconds, ms_per_step_hint, gpu_index, uuid, pairs
     return out
 
 
-def culled_entry(workload, ctx, dev, flush, steps, warmup, scaling, brute_loss, brute_ms):
+def culled_entry(workload, ctx, dev, flush, steps, warmup, scaling, brute_loss, brute_ms, late_fit_steps=0):
     """The workload on RelaxationEngine(cull=True): k-d leaf order at set-up, bounds seeded by the previous step's arg-mins,
     bit-identical search results (tests/test_cull_gpu.py); reports ms/step and the fraction of blocks evaluated."""
     import torch
@@ -436,11 +436,31 @@ def culled_entry(workload, ctx, dev, flush, steps, warmup, scaling, brute_loss, 
     for _ in range(5):
         engine.step()
     st = engine.culling_stats()
+    late = None
+    if late_fit_steps:
+        # the timed steps above are the first of a fit (tau = 5: every point follows a random part each step, so the seeds
+        # are poor).  The same engine further into a fit: a compressed cosine schedule 5 -> 1 over `late_fit_steps` steps,
+        # then K more timed steps at the end state.  The brute-force step costs the same at any state.
+        from reart_b200.engine import tau_schedule
+        done = engine.iteration
+        for i in range(done, late_fit_steps):
+            engine.step(tau_schedule(i, late_fit_steps, 5.0, 1.0))
+        engine.culling_stats()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        torch.cuda.synchronize()
+        for i in range(steps):
+            flush.fill_(i & 0xff)
+            ev[i][0].record(); l_late = engine.step(1.0); ev[i][1].record()
+        torch.cuda.synchronize()
+        st2 = engine.culling_stats()
+        ms2 = sum(a.elapsed_time(b) for a, b in ev) / steps
+        late = {"after_steps": late_fit_steps, "tau": 1.0, "ms_per_step": ms2, "speedup_vs_brute_force_step": brute_ms / ms2,
+                "fraction_evaluated": (st2[0] / st2[1]) if st2 and st2[1] else None, "loss": float(l_late.item())}
     engine.release()
     del engine
     torch.cuda.empty_cache()
     pairs = 2.0 * T_total * N * N
-    return {"enabled_in_headline": False, "ms_per_step": ms, "value": pairs / (ms * 1e-3), "unit": UNIT,
+    return {"enabled_in_headline": False, "ms_per_step": ms, "value": pairs / (ms * 1e-3), "unit": UNIT, "late_in_a_fit": late,
             "speedup_vs_brute_force_step": brute_ms / ms, "final_loss": final, "final_loss_brute_force": brute_loss,
             "block_pairs_evaluated": st[0] if st else None, "block_pairs_offered": st[1] if st else None,
             "fraction_evaluated": (st[0] / st[1]) if st and st[1] else None,
@@ -653,7 +673,8 @@ def main():
     culling = None
     if args.workload != "cfg4":
         try:
-            culling = culled_entry(args.workload, ctx, dev, flush, K, W, args.scaling, final_loss, ms_per_step)
+            culling = culled_entry(args.workload, ctx, dev, flush, K, W, args.scaling, final_loss, ms_per_step,
+                                   late_fit_steps=600 if (world == 1 and args.workload == "cfg3_16k" and not args.no_sweep) else 0)
         except Exception as exc:
             culling = {"error": f"{type(exc).__name__}: {exc}"}
 

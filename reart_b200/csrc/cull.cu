@@ -18,6 +18,7 @@
 namespace reart {
 
 constexpr int kCullRowChunk = 256;
+constexpr int kCullSeeds = 4;                                 // neighbours on each side whose seeds are also tried
 
 __global__ void __launch_bounds__(kCullRowChunk) cull_row_bounds_kernel(const CullParams p, int row_chunks) {
     __shared__ unsigned s_w[kCullRowChunk / 32];
@@ -25,13 +26,24 @@ __global__ void __launch_bounds__(kCullRowChunk) cull_row_bounds_kernel(const Cu
     const int i = rc * kCullRowChunk + threadIdx.x;
     unsigned bits = 0u;                                        // distances are >= 0: their bit patterns order like the floats
     if (i < p.na) {
-        const int j = p.nn_rows ? p.nn_rows[(int64_t)b * p.na + i] : -1;
+        // candidates: the row's own previous arg-min and those of its neighbours in the caller's point order (spatial
+        // neighbours when the caller sorted the cloud, engine.py) -- a point that changed part since the last step has a
+        // useless seed of its own, but a neighbour that already belongs to the new part has a good one.  ANY real target
+        // bounds the minimum from above, so the smallest of the candidates is still an exact bound.
         float ub = INFINITY;
-        if (j >= 0 && j < p.nb) {
+        if (p.nn_rows) {
             const float* a = p.a + ((int64_t)b * p.na + i) * 3;
-            const float* t = p.b + ((int64_t)b * p.nb + j) * 3;
-            ub = sqdist_scalar(a[0], a[1], a[2], t[0], t[1], t[2]);
-            if (!(ub >= 0.f)) ub = INFINITY;                   // NaN input: no culling
+            const float ax = a[0], ay = a[1], az = a[2];
+#pragma unroll
+            for (int d = -kCullSeeds; d <= kCullSeeds; ++d) {
+                const int in = min(max(i + d, 0), p.na - 1);
+                const int j = p.nn_rows[(int64_t)b * p.na + in];
+                if (j >= 0 && j < p.nb) {
+                    const float* t = p.b + ((int64_t)b * p.nb + j) * 3;
+                    const float c = sqdist_scalar(ax, ay, az, t[0], t[1], t[2]);
+                    if (c < ub) ub = c;                        // NaN never passes: no culling on NaN input
+                }
+            }
         }
         bits = __float_as_uint(ub);
     }
@@ -59,12 +71,24 @@ __global__ void __launch_bounds__(256) cull_col_boxes_kernel(const CullParams p,
         const float* t = p.b + ((int64_t)b * p.nb + j) * 3;
         const float x = t[0], y = t[1], z = t[2];
         lx = hx = x; ly = hy = y; lz = hz = z;
-        const int i = p.nn_cols ? p.nn_cols[(int64_t)b * p.nb + j] : -1;
+        // candidates: the previous arg-min rows of this target and of its neighbours in the caller's order, and the rows
+        // next to the own one (a row that changed part moved away; its neighbours in the canonical order mostly did not)
         float ub = INFINITY;
-        if (i >= 0 && i < p.na) {
-            const float* a = p.a + ((int64_t)b * p.na + i) * 3;
-            ub = sqdist_scalar(a[0], a[1], a[2], x, y, z);
-            if (!(ub >= 0.f)) ub = INFINITY;
+        if (p.nn_cols) {
+#pragma unroll
+            for (int d = -kCullSeeds; d <= kCullSeeds; ++d) {
+                const int jn = min(max(j + d, 0), p.nb - 1);
+                const int i0 = p.nn_cols[(int64_t)b * p.nb + jn];
+                if (i0 < 0 || i0 >= p.na) continue;
+#pragma unroll
+                for (int e = -1; e <= 1; ++e) {
+                    if (d != 0 && e != 0) continue;            // row neighbours only around the target's own seed
+                    const int i = min(max(i0 + e, 0), p.na - 1);
+                    const float* a = p.a + ((int64_t)b * p.na + i) * 3;
+                    const float c = sqdist_scalar(a[0], a[1], a[2], x, y, z);
+                    if (c < ub) ub = c;
+                }
+            }
         }
         bits = __float_as_uint(ub);
     }

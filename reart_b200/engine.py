@@ -185,8 +185,10 @@ class RelaxationEngine(_EngineBase):
         self.perm_cano = self.perm_frames = None
         cano_orig, frames_orig = self.cano, self.frames
         if self.cull:
-            self.perm_cano = ops.kd_order(self.cano[None], 256)[0]
-            self.perm_frames = ops.kd_order(self.frames, 32)
+            # k-d order refined well below the chunk sizes of the search (256 rows / 32 targets): the chunks stay the same
+            # compact sets, and consecutive points become nearest neighbours -- whose arg-mins cull.cu tries as extra seeds
+            self.perm_cano = ops.kd_order(self.cano[None], 8)[0]
+            self.perm_frames = ops.kd_order(self.frames, 4)
             self.cano = self.cano[self.perm_cano].contiguous()
             self.frames = torch.gather(self.frames, 1, self.perm_frames[:, :, None].expand(-1, -1, 3)).contiguous()
         self.frames_packed = ops.pack_cloud(self.frames)          # constant over the optimisation: packed once
