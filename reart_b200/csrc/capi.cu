@@ -336,6 +336,7 @@ static int energy_pipeline(const float* cano, const float* W, const float* hot, 
         cp.a = skinned; cp.b = tgt; cp.nn_rows = nn_rows; cp.nn_cols = nn_cols;
         cp.B = (int)T; cp.na = (int)N; cp.nb = (int)M; cp.nb_pad = (int)padded_points(M);
         cp.colbox = colbox; cp.rowbound = rowbound;
+        cp.coarse = (N >= 8192 && M >= 8192 && N <= 800000 && M <= 800000) ? 1 : 0;   // small clouds: the pass costs more than it saves
         rc = launch_cull_bounds(cp, stream);
         if (rc) return rc;
         sp.cull = 1; sp.colbox = colbox; sp.rowbound = rowbound;

@@ -14,16 +14,76 @@
 // both clouds into k-d leaves once; any order is correct.
 #include "common.cuh"
 #include "kernels.h"
+#include <algorithm>
 
 namespace reart {
 
 constexpr int kCullRowChunk = 256;
 constexpr int kCullSeeds = 4;                                 // neighbours on each side whose seeds are also tried
+constexpr int kCoarse = 256;                                  // points per level-A representative of the coarse descent
 
-__global__ void __launch_bounds__(kCullRowChunk) cull_row_bounds_kernel(const CullParams p, int row_chunks) {
+// History-free upper bound of min_j d(q, pts_j): a three-level descent over the caller's point order (spatially coherent
+// when the caller sorted the cloud): (A) one representative per 256 points, staged in shared memory by the block -> the two
+// best; (B) the 8 representatives (one per 32 points) of the best (and a close runner-up) -> the best 32-point chunk; (C)
+// every point of it.
+// Every candidate is a real point of the cloud and the distance is the search's own arithmetic, so whatever the descent
+// finds bounds the computed minimum from above; how tight it is only decides how much is culled.  ~ n/256 + 8..16 + 32
+// evaluations per query instead of n.
+__device__ __forceinline__ float coarse_upper_bound(const float* __restrict__ pts, int n, const float* __restrict__ s_rep,
+                                                    int nrep, float qx, float qy, float qz) {
+    float a0 = INFINITY, a1 = INFINITY;
+    int r0 = 0, r1 = 0;
+    for (int r = 0; r < nrep; ++r) {
+        const float d = sqdist_scalar(qx, qy, qz, s_rep[3 * r], s_rep[3 * r + 1], s_rep[3 * r + 2]);
+        if (d < a0) { a1 = a0; r1 = r0; a0 = d; r0 = r; }
+        else if (d < a1) { a1 = d; r1 = r; }
+    }
+    float ub = a0;                                             // the representatives are real points
+    // (B) the 8 chunk representatives of the best 256-point group (and of the runner-up only when it is close: within 2x
+    // in distance), (C) every point of the best chunk -- the global-memory part of the descent, ~20 sectors per query
+    float b0 = INFINITY;
+    int c0 = -1;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        const int r = h ? r1 : r0;
+        if (h && (r1 == r0 || !(a1 < 4.0f * a0))) break;
+        for (int k = 0; k < kCoarse / kChunk; ++k) {
+            const int c = r * (kCoarse / kChunk) + k;
+            if (c * kChunk >= n) break;
+            const int j = min(c * kChunk + kChunk / 2, n - 1);
+            const float* t = pts + (int64_t)j * 3;
+            const float d = sqdist_scalar(qx, qy, qz, t[0], t[1], t[2]);
+            if (d < b0) { b0 = d; c0 = c; }
+        }
+    }
+    ub = fminf(ub, b0);
+    if (c0 >= 0) {
+        const int j0 = c0 * kChunk, j1 = min(j0 + kChunk, n);
+        for (int j = j0; j < j1; ++j) {
+            const float* t = pts + (int64_t)j * 3;
+            ub = fminf(ub, sqdist_scalar(qx, qy, qz, t[0], t[1], t[2]));
+        }
+    }
+    return ub;                                                 // NaN coordinates give NaN -> the callers turn that into +inf
+}
+
+// stage the level-A representatives of one cloud [n,3]: point min(256 r + 128, n - 1) for r < ceil(n / 256)
+__device__ __forceinline__ void coarse_stage(const float* __restrict__ pts, int n, float* s_rep, int nrep) {
+    for (int e = threadIdx.x; e < nrep * 3; e += blockDim.x) {
+        const int r = e / 3, k = e - 3 * r;
+        s_rep[e] = pts[(int64_t)min(r * kCoarse + kCoarse / 2, n - 1) * 3 + k];
+    }
+}
+
+__global__ void __launch_bounds__(kCullRowChunk) cull_row_bounds_kernel(const CullParams p, int row_chunks, int nrep) {
+    extern __shared__ float s_rep[];                           // coarse: [nrep][3] representatives of this frame's targets
     __shared__ unsigned s_w[kCullRowChunk / 32];
     const int rc = blockIdx.x, b = blockIdx.y;
     const int i = rc * kCullRowChunk + threadIdx.x;
+    if (p.coarse) {
+        coarse_stage(p.b + (int64_t)b * p.nb * 3, p.nb, s_rep, nrep);
+        __syncthreads();
+    }
     unsigned bits = 0u;                                        // distances are >= 0: their bit patterns order like the floats
     if (i < p.na) {
         // candidates: the row's own previous arg-min and those of its neighbours in the caller's point order (spatial
@@ -31,9 +91,13 @@ __global__ void __launch_bounds__(kCullRowChunk) cull_row_bounds_kernel(const Cu
         // useless seed of its own, but a neighbour that already belongs to the new part has a good one.  ANY real target
         // bounds the minimum from above, so the smallest of the candidates is still an exact bound.
         float ub = INFINITY;
+        const float* a = p.a + ((int64_t)b * p.na + i) * 3;
+        const float ax = a[0], ay = a[1], az = a[2];
+        if (p.coarse) {
+            ub = coarse_upper_bound(p.b + (int64_t)b * p.nb * 3, p.nb, s_rep, nrep, ax, ay, az);
+            if (!(ub >= 0.f)) ub = INFINITY;                   // NaN input: no culling
+        }
         if (p.nn_rows) {
-            const float* a = p.a + ((int64_t)b * p.na + i) * 3;
-            const float ax = a[0], ay = a[1], az = a[2];
 #pragma unroll
             for (int d = -kCullSeeds; d <= kCullSeeds; ++d) {
                 const int in = min(max(i + d, 0), p.na - 1);
@@ -59,11 +123,17 @@ __global__ void __launch_bounds__(kCullRowChunk) cull_row_bounds_kernel(const Cu
 }
 
 // one warp per 32-target chunk
-__global__ void __launch_bounds__(256) cull_col_boxes_kernel(const CullParams p, int chunks_total) {
+__global__ void __launch_bounds__(256) cull_col_boxes_kernel(const CullParams p, int chunks_total, int nrep) {
+    extern __shared__ float s_rep[];                           // coarse: [nrep][3] representatives of this frame's rows
     const int lane = threadIdx.x & 31;
-    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= (int64_t)p.B * chunks_total) return;
-    const int b = (int)(w / chunks_total), cc = (int)(w - (int64_t)b * chunks_total);
+    const int b = blockIdx.y;
+    if (p.coarse) {
+        coarse_stage(p.a + (int64_t)b * p.na * 3, p.na, s_rep, nrep);
+        __syncthreads();
+    }
+    const int cc = (int)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (cc >= chunks_total) return;
+    const int64_t w = (int64_t)b * chunks_total + cc;
     const int j = cc * kChunk + lane;
     float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
     unsigned bits = 0u;
@@ -74,6 +144,10 @@ __global__ void __launch_bounds__(256) cull_col_boxes_kernel(const CullParams p,
         // candidates: the previous arg-min rows of this target and of its neighbours in the caller's order, and the rows
         // next to the own one (a row that changed part moved away; its neighbours in the canonical order mostly did not)
         float ub = INFINITY;
+        if (p.coarse) {
+            ub = coarse_upper_bound(p.a + (int64_t)b * p.na * 3, p.na, s_rep, nrep, x, y, z);
+            if (!(ub >= 0.f)) ub = INFINITY;
+        }
         if (p.nn_cols) {
 #pragma unroll
             for (int d = -kCullSeeds; d <= kCullSeeds; ++d) {
@@ -112,10 +186,12 @@ int launch_cull_bounds(const CullParams& p, cudaStream_t stream) {
     const int row_chunks = (int)ceil_div(p.na, kCullRowChunk);
     const int chunks_total = p.nb_pad / kChunk;
     dim3 grid((unsigned)row_chunks, (unsigned)p.B);
-    cull_row_bounds_kernel<<<grid, kCullRowChunk, 0, stream>>>(p, row_chunks);
+    const int nrep_b = p.coarse ? (int)ceil_div(p.nb, kCoarse) : 0, nrep_a = p.coarse ? (int)ceil_div(p.na, kCoarse) : 0;
+    if ((size_t)std::max(nrep_a, nrep_b) * 12 > 40 * 1024) return kErrUnsupported;      // clouds beyond 873 k points: no coarse bounds
+    cull_row_bounds_kernel<<<grid, kCullRowChunk, (size_t)nrep_b * 12, stream>>>(p, row_chunks, nrep_b);
     REART_CHECK_LAUNCH();
-    const int64_t warps = (int64_t)p.B * chunks_total;
-    cull_col_boxes_kernel<<<(unsigned)ceil_div(warps, 8), 256, 0, stream>>>(p, chunks_total);
+    dim3 cgrid((unsigned)ceil_div(chunks_total, 8), (unsigned)p.B);
+    cull_col_boxes_kernel<<<cgrid, 256, (size_t)nrep_a * 12, stream>>>(p, chunks_total, nrep_a);
     REART_CHECK_LAUNCH();
     return kOk;
 }

@@ -69,6 +69,7 @@ struct CullParams {
     int B, na, nb, nb_pad;
     float* colbox;                // out [B, nb_pad/32, 8]
     float* rowbound;              // out [B, ceil(na/256)]
+    int coarse;                   // 1: also bound every point by a history-free coarse descent over the other cloud (cull.cu)
 };
 int launch_cull_bounds(const CullParams& p, cudaStream_t stream);
 

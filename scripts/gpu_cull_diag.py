@@ -33,3 +33,36 @@ for steps, label in ((20, "early (20 steps, tau~5)"), (600, "late (600 steps, ta
     ubc = (fr - torch.gather(sk, 1, nn_cols[:, :, None].expand(-1, -1, 3))).square().sum(-1)
     chc = ubc.reshape(T, N // 32, 32).sqrt().sort(dim=-1).values
     print(f"{label} | columns own seed | chunk max median {chchc if False else chc[..., 31].median():.4f} | 30th {chc[..., 29].median():.4f} | median {chc[..., 16].median():.4f}", flush=True)
+
+# ---- how much could be culled at this (late) state?  fraction of (256-row chunk, 32-target chunk) blocks evaluated under
+# different bounds, with the actual chunk boxes
+def boxes(x, chunk):
+    c = x.reshape(x.shape[0], -1, chunk, 3)
+    return c.amin(2), c.amax(2)
+def fraction(sk, fr, rb, cb):
+    rlo, rhi = boxes(sk, 256); clo, chi = boxes(fr, 32)
+    tot = ev = 0
+    for t in range(sk.shape[0]):
+        g = torch.clamp(torch.maximum(rlo[t][:, None] - chi[t][None], clo[t][None] - rhi[t][:, None]), min=0).square().sum(-1)   # [R,C]
+        e = (g <= rb[t][:, None]) | (g <= cb[t][None])
+        tot += e.numel(); ev += int(e.sum())
+    return ev / tot
+sk, fr = eng.skinned, eng.frames
+d2 = torch.stack([torch.cdist(sk[t:t+1], fr[t:t+1])[0].square() for t in range(T)])          # [T,N,N]
+true_r, true_c = d2.min(2).values, d2.min(1).values
+rb_true = true_r.reshape(T, -1, 256).amax(-1); cb_true = true_c.reshape(T, -1, 32).amax(-1)
+rb_seed = ub5.reshape(T, -1, 256).amax(-1); cb_seed = ubc.reshape(T, -1, 32).amax(-1)
+print("late: fraction evaluated with the seed bounds (5 row seeds, 1 column seed): %.3f" % fraction(sk, fr, rb_seed, cb_seed))
+print("late: fraction evaluated with EXACT bounds (true NN distances, the floor for these boxes): %.3f" % fraction(sk, fr, rb_true, cb_true))
+q = 0.97
+rb_q = true_r.reshape(T, -1, 256).sort(-1).values[..., int(256 * q) - 1]
+print("late: ... exact bounds but ignoring the worst 3 %% of rows per chunk: %.3f" % fraction(sk, fr, rb_q, cb_true))
+# rows regrouped per frame by posed position (k-d order of the POSED cloud): the floor with compact row boxes
+from reart_b200 import ops
+fr_f = []
+for t in range(T):
+    perm = ops.kd_order(sk[t:t+1], 8)[0]
+    fr_f.append(perm)
+perm = torch.stack(fr_f)
+sk2 = torch.gather(sk, 1, perm[:, :, None].expand(-1, -1, 3)); tr2 = torch.gather(true_r, 1, perm)
+print("late: exact bounds, rows regrouped per frame on the posed cloud: %.3f" % fraction(sk2, fr, tr2.reshape(T, -1, 256).amax(-1), cb_true))

@@ -74,10 +74,12 @@ def test_culled_evaluation_is_bit_identical_and_skips_work(T, N, P, ordered):
     nn = (torch.full((T, N), -1, dtype=torch.int32, device=dev()), torch.full((T, M), -1, dtype=torch.int32, device=dev()),
           torch.zeros(2, dtype=torch.int64, device=dev()))
     brute = evaluate(cano, W, R, tr, frames)
-    first = evaluate(cano, W, R, tr, frames, nn)                       # no seeds yet: infinite bounds, nothing skipped
+    first = evaluate(cano, W, R, tr, frames, nn)                       # no seeds yet
     same(brute, first)
     ev, off = nn[2].tolist()
-    assert ev == off and off > 0
+    # small clouds: infinite bounds, nothing skipped; from 8192 points on the history-free coarse bounds of cull.cu already
+    # cull on the very first evaluation
+    assert off > 0 and (ev == off if min(N, M) < 8192 else ev < off)
     assert torch.equal(nn[0].long(), brute["i_f"]) and torch.equal(nn[1].long(), brute["i_b"])   # the seeds ARE the arg-mins
     # the optimiser moves the poses a little; seeds from the previous evaluation
     g = torch.Generator(device="cuda").manual_seed(3)
