@@ -357,7 +357,9 @@ constexpr int kCullTileChunks = 16;
 constexpr int kCullTileBytes = kCullTileChunks * kChunk * 12;
 constexpr int kCullStageBytes = kCullTileBytes + kCullTileChunks * kBoxFloats * 4;
 
-__global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_cull_kernel(const SymParams p) {
+template <int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) chamfer_sym_cull_kernel(const SymParams p) {
+    constexpr int kWarps = NT / 32;
     constexpr int R = 8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kCullStages];
@@ -369,7 +371,7 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_cull_kernel(const 
     const int split = item % p.splits;
     const int b = item / p.splits;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int qbase = qb * (R * kSymThreads);
+    const int qbase = qb * (R * NT);
     const float* __restrict__ q = p.a + (int64_t)b * p.na * 3;
 
     const int chunks_total = p.nb_pad / kChunk;
@@ -485,7 +487,7 @@ __global__ void __launch_bounds__(kSymThreads, 2) chamfer_sym_cull_kernel(const 
         __syncwarp();
         if (lane == 0) {
             __threadfence_block();
-            if (atomicAdd(&done_cnt[st], 1u) == (unsigned)(kSymWarps - 1)) {
+            if (atomicAdd(&done_cnt[st], 1u) == (unsigned)(kWarps - 1)) {
                 done_cnt[st] = 0u;
                 __threadfence_block();
                 if (k + kCullStages < ntiles) {
@@ -588,8 +590,16 @@ static int launch_sym_rs(SymParams& p, cudaStream_t stream) {
 
 static int launch_sym_cull(SymParams& p, cudaStream_t stream) {
     using C = SymCfg<8, 1>;
-    p.qblocks = (int)ceil_div(p.na, 8 * kSymThreads);
-    p.splits = sym_choose_splits(p.B, p.qblocks, p.nb_pad / kChunk, C::kTileChunks);
+    const int nt = (p.variant == 2) ? 256 : 128;               // 4 warps per CTA, 4 CTAs per SM: less idle time at the end of an item
+    p.qblocks = (int)ceil_div(p.na, 8 * nt);
+    {
+        // item durations vary with what survives the culling, so wave arithmetic is moot: aim at ~8 items per CTA slot for
+        // the hardware scheduler to balance, but keep >= 2 tiles per item (prologue amortised, room for the warps to drift)
+        const int64_t slots = (int64_t)(512 / nt) * 148, base = std::max<int64_t>(1, (int64_t)p.B * p.qblocks);
+        const int chunks_total = p.nb_pad / kChunk;
+        const int64_t want = ceil_div(8 * slots, base), cap = std::max(1, chunks_total / (2 * kCullTileChunks));
+        p.splits = (int)std::max<int64_t>(1, std::min(want, cap));
+    }
     p.col_chunk_pts = C::kColChunkPts;
     const int64_t items = (int64_t)p.B * p.qblocks * p.splits;
     if (items <= 0) return kOk;
@@ -607,7 +617,8 @@ static int launch_sym_cull(SymParams& p, cudaStream_t stream) {
         }
     }
     const size_t smem = (size_t)kCullStages * kCullStageBytes;
-    chamfer_sym_cull_kernel<<<(unsigned)items, kSymThreads, smem, stream>>>(p);
+    if (nt == 256) chamfer_sym_cull_kernel<256><<<(unsigned)items, 256, smem, stream>>>(p);
+    else chamfer_sym_cull_kernel<128><<<(unsigned)items, 128, smem, stream>>>(p);
     REART_CHECK_LAUNCH();
     return kOk;
 }
