@@ -59,9 +59,22 @@ __device__ __forceinline__ float coarse_upper_bound(const float* __restrict__ pt
     ub = fminf(ub, b0);
     if (c0 >= 0) {
         const int j0 = c0 * kChunk, j1 = min(j0 + kChunk, n);
-        for (int j = j0; j < j1; ++j) {
-            const float* t = pts + (int64_t)j * 3;
-            ub = fminf(ub, sqdist_scalar(qx, qy, qz, t[0], t[1], t[2]));
+        if (j1 - j0 == kChunk && ((reinterpret_cast<uintptr_t>(pts + (int64_t)j0 * 3) & 15) == 0)) {
+            // a full chunk is 384 contiguous bytes: 24 vector loads instead of 96 scalar ones, four points per three float4
+            const float4* v = reinterpret_cast<const float4*>(pts + (int64_t)j0 * 3);
+#pragma unroll 2
+            for (int g = 0; g < kChunk / 4; ++g) {
+                const float4 A = __ldg(v + 3 * g), B = __ldg(v + 3 * g + 1), C = __ldg(v + 3 * g + 2);
+                ub = fminf(ub, sqdist_scalar(qx, qy, qz, A.x, A.y, A.z));
+                ub = fminf(ub, sqdist_scalar(qx, qy, qz, A.w, B.x, B.y));
+                ub = fminf(ub, sqdist_scalar(qx, qy, qz, B.z, B.w, C.x));
+                ub = fminf(ub, sqdist_scalar(qx, qy, qz, C.y, C.z, C.w));
+            }
+        } else {
+            for (int j = j0; j < j1; ++j) {
+                const float* t = pts + (int64_t)j * 3;
+                ub = fminf(ub, sqdist_scalar(qx, qy, qz, t[0], t[1], t[2]));
+            }
         }
     }
     return ub;                                                 // NaN coordinates give NaN -> the callers turn that into +inf
@@ -98,10 +111,13 @@ __global__ void __launch_bounds__(kCullRowChunk) cull_row_bounds_kernel(const Cu
             if (!(ub >= 0.f)) ub = INFINITY;                   // NaN input: no culling
         }
         if (p.nn_rows) {
+            int jprev = -2;
 #pragma unroll
             for (int d = -kCullSeeds; d <= kCullSeeds; ++d) {
                 const int in = min(max(i + d, 0), p.na - 1);
                 const int j = p.nn_rows[(int64_t)b * p.na + in];
+                if (j == jprev) continue;                      // neighbours very often share a seed
+                jprev = j;
                 if (j >= 0 && j < p.nb) {
                     const float* t = p.b + ((int64_t)b * p.nb + j) * 3;
                     const float c = sqdist_scalar(ax, ay, az, t[0], t[1], t[2]);
