@@ -133,13 +133,13 @@ REART_API int reart_skinned_chamfer_fwd_bwd_ex(const float* cano, const float* W
                                             float* g_skinned, int compute_grad, float* d_fwd,
                                                int64_t* i_fwd, float* d_bwd, int64_t* i_bwd, void* workspace,
                                             int64_t workspace_bytes, void* stream);
-/* The same evaluation with EXACT tile culling (csrc/cull.cu, chamfer_sym.cu CULL): nn_rows [T,N] / nn_cols [T,M] int32
- * carry the arg-mins from one call to the next (fill with -1 before the first call: that call is the brute-force
- * search); they seed upper bounds of every minimum, and (256-row, 32-target) blocks whose bounding-box gap exceeds both
- * bounds are skipped.  Loss, distances, indices and gradients are bit-identical to reart_skinned_chamfer_fwd_bwd_ex for
- * ANY point order; how much is skipped depends on how spatially compact consecutive points are (engine.py sorts both
- * clouds into k-d leaves once).  cull_stats (optional, device, [2] uint64, caller-zeroed): += (warp, chunk) pairs
- * evaluated / offered.  Either nn pointer null: no culling. */
+/* The same evaluation with EXACT tile culling (csrc/cull.cu, chamfer_sym.cu: chamfer_sym_cull_kernel): nn_rows [T,N] /
+ * nn_cols [T,M] int32 carry the arg-mins from one call to the next (fill with -1 before the first call); together with a
+ * history-free coarse descent (clouds of >= 8192 points) they give upper bounds of every minimum, and (256-row, 32-target)
+ * blocks whose bounding-box gap is strictly above both bounds are skipped.  Loss, distances, indices and gradients are
+ * bit-identical to reart_skinned_chamfer_fwd_bwd_ex for ANY point order and ANY seed values; how much is skipped depends on
+ * how spatially compact consecutive points are (engine.py sorts both clouds into a k-d order once).  cull_stats (optional,
+ * device, [2] uint64, caller-zeroed): += (warp, chunk) pairs evaluated / offered.  Either nn pointer null: no culling. */
 REART_API int reart_skinned_chamfer_fwd_bwd_culled(const float* cano, const float* W, const float* R, const float* tr,
                                                    const float* tgt, const float* tgt_packed, int64_t T, int64_t N,
                                                    int64_t M, int64_t P, float* skinned, double* loss, float* gW,

@@ -1,17 +1,20 @@
 // cull.cu -- the static bounds the culled search schedule (chamfer_sym.cu, CULL = true) tests against.
 //
-// The brute-force search evaluates every (skinned point, observed point) pair of a frame; an optimisation moves the
-// clouds a little per iteration, so the nearest neighbours of the PREVIOUS evaluation are excellent candidates now:
-//   ub_i = d(a_i, b[nn_prev(i)])  >=  min_j d(a_i, b_j)          (any real target bounds the minimum from above)
-// and likewise per observed point.  One pass turns them into
+// The brute-force search evaluates every (skinned point, observed point) pair of a frame.  ANY real point of the other
+// cloud bounds a point's minimum from above, and two cheap sources give good ones:
+//   * history: an optimisation moves the clouds a little per iteration, so the arg-mins of the PREVIOUS evaluation -- the
+//     point's own and those of its neighbours in the caller's point order -- are excellent candidates now
+//         ub_i = min over candidates j of d(a_i, b_j)  >=  min_j d(a_i, b_j);
+//   * no history: a three-level descent over the other cloud (coarse_upper_bound below), for clouds of >= 8192 points.
+// One pass per side turns them into
 //   rowbound[b][rc]  = max of ub over the 256 rows of row chunk rc   (one warp of the search owns exactly these rows)
 //   colbox[b][cc]    = bounding box of the 32 targets of chunk cc, and the max of ub over them,
 // and the search skips a (row chunk, target chunk) pair whose box-to-box squared gap -- a lower bound of every computed
-// pair distance in it -- is STRICTLY above both bounds: such a pair can hold neither a minimum nor a tie.  The first
-// evaluation (no history, nn = -1) gets infinite bounds and is the brute-force search.  The distances here use the very
-// arithmetic of the search (sqdist_scalar), so the bounds bound the COMPUTED minima and the culled keys are bit-identical.
-// How much is skipped depends on how compact the chunks are: callers that control the point order (engine.py) sort
-// both clouds into k-d leaves once; any order is correct.
+// pair distance in it -- is STRICTLY above both bounds: such a pair can hold neither a minimum nor a tie.  Without seeds
+// (nn = -1) and below 8192 points the bounds are infinite and the search is the brute force.  The distances here use the
+// very arithmetic of the search (sqdist_scalar), so the bounds bound the COMPUTED minima and the culled keys are
+// bit-identical.  How much is skipped depends on how compact the chunks are: callers that control the point order
+// (engine.py) sort both clouds into a k-d order once; any order is correct.
 #include "common.cuh"
 #include "kernels.h"
 #include <algorithm>
