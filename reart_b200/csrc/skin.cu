@@ -149,6 +149,112 @@ __global__ void __launch_bounds__(kSortBlock) skin_fwd_sorted_kernel(const float
     }
 }
 
+// Eight frames per CTA, sorted by WARPS: phase 1, thread = point, skins its point for all 8 frames into shared memory and
+// writes the AoS rows; ONE barrier; phase 2, warp f sorts frame f's 256 keys by itself (8 keys per lane, register swaps and
+// shuffles, common.cuh warp_bitonic_sort256) and writes the sorted block, perm and the quantile index.  The block-wide
+// hybrid sort above needs 12 barriers per frame; this is 2 per 8 frames.  Same keys, same arithmetic: identical output.
+constexpr int kSortFrames = 8;
+
+__global__ void __launch_bounds__(kSortBlock) skin_fwd_sorted8_kernel(const float* __restrict__ cano,
+                                                                      const float* __restrict__ W,
+                                                                      const float* __restrict__ R,
+                                                                      const float* __restrict__ tr, int T, int N, int P,
+                                                                      float* __restrict__ out,
+                                                                      float* __restrict__ out_packed,
+                                                                      unsigned char* __restrict__ perm,
+                                                                      float* __restrict__ xq, int n_pad) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    float* sx = reinterpret_cast<float*>(sm_raw);                             // [8 frames][3][256]
+    float* sm_tf = sx + kSortFrames * 3 * kSortBlock;                         // [8][P][12]
+    const int t0 = blockIdx.y * kSortFrames;
+    const int nt = min(kSortFrames, T - t0);
+    for (int e = threadIdx.x; e < nt * P * 12; e += blockDim.x) {
+        const int f = e / (P * 12), rem = e - f * P * 12, p = rem / 12, k = rem - p * 12;
+        const int64_t tp = (int64_t)(t0 + f) * P + p;
+        sm_tf[e] = (k < 9) ? R[tp * 9 + k] : tr[tp * 3 + (k - 9)];
+    }
+    __syncthreads();
+    const int i = threadIdx.x;
+    const int base = blockIdx.x * kSortBlock;
+    const int n = base + i;
+    const bool real = n < N;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (real) { cx = cano[3 * n]; cy = cano[3 * n + 1]; cz = cano[3 * n + 2]; }
+    const float* __restrict__ w = W + (int64_t)(real ? n : 0) * P;
+    // the weight row is read ONCE: rows with at most two non-zeros (one-hot / straight-through rows have one) are kept in
+    // registers for all 8 frames; denser rows re-read it per frame.  Non-zeros are applied in increasing p either way.
+    int p0 = 0, p1 = 0, nnz = 0;
+    float w0 = 0.f, w1 = 0.f;
+    if (real) {
+        for (int p = 0; p < P; ++p) {
+            const float wp = __ldg(w + p);
+            if (wp != 0.f) {
+                if (nnz == 0) { p0 = p; w0 = wp; }
+                else if (nnz == 1) { p1 = p; w1 = wp; }
+                ++nnz;
+            }
+        }
+    }
+    for (int f = 0; f < nt; ++f) {
+        float ax = INFINITY, ay = INFINITY, az = INFINITY;                    // padding sorts last
+        if (real) {
+            ax = ay = az = 0.f;
+            const float* tf = sm_tf + f * P * 12;
+            if (nnz <= 2) {
+                if (nnz >= 1) {
+                    const float* m = tf + p0 * 12;
+                    ax = __fmaf_rn(w0, skin_axis(cx, cy, cz, m[0], m[1], m[2], m[9]), ax);
+                    ay = __fmaf_rn(w0, skin_axis(cx, cy, cz, m[3], m[4], m[5], m[10]), ay);
+                    az = __fmaf_rn(w0, skin_axis(cx, cy, cz, m[6], m[7], m[8], m[11]), az);
+                }
+                if (nnz == 2) {
+                    const float* m = tf + p1 * 12;
+                    ax = __fmaf_rn(w1, skin_axis(cx, cy, cz, m[0], m[1], m[2], m[9]), ax);
+                    ay = __fmaf_rn(w1, skin_axis(cx, cy, cz, m[3], m[4], m[5], m[10]), ay);
+                    az = __fmaf_rn(w1, skin_axis(cx, cy, cz, m[6], m[7], m[8], m[11]), az);
+                }
+            } else {
+                for (int p = 0; p < P; ++p) {
+                    const float wp = __ldg(w + p);
+                    if (wp != 0.f) {
+                        const float* m = tf + p * 12;
+                        ax = __fmaf_rn(wp, skin_axis(cx, cy, cz, m[0], m[1], m[2], m[9]), ax);
+                        ay = __fmaf_rn(wp, skin_axis(cx, cy, cz, m[3], m[4], m[5], m[10]), ay);
+                        az = __fmaf_rn(wp, skin_axis(cx, cy, cz, m[6], m[7], m[8], m[11]), az);
+                    }
+                }
+            }
+            float* o = out + ((int64_t)(t0 + f) * N + n) * 3;
+            o[0] = ax; o[1] = ay; o[2] = az;
+        }
+        float* s = sx + f * 3 * kSortBlock;
+        s[i] = ax; s[kSortBlock + i] = ay; s[2 * kSortBlock + i] = az;
+    }
+    __syncthreads();
+    const int f = threadIdx.x >> 5, lane = threadIdx.x & 31;                  // warp f owns frame t0 + f
+    if (f >= nt) return;
+    const float* s = sx + f * 3 * kSortBlock;
+    u64 key[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int e = lane * 8 + r;
+        key[r] = ((u64)orderable_bits(s[e]) << 32) | (u64)e;
+    }
+    warp_bitonic_sort256(key, lane);
+    const int nblk = n_pad / kSortBlock;
+    float* sorted_b = out_packed + (int64_t)(t0 + f) * n_pad * 3;
+    unsigned long long pm = 0ull;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int src = (int)(key[r] & 0xffu), pos = lane * 8 + r;
+        const float sxv = s[src];
+        sorted_block_store(sorted_b, blockIdx.x, pos, sxv, s[kSortBlock + src], s[2 * kSortBlock + src]);
+        pm |= (unsigned long long)src << (8 * r);
+        if (r == 7 && (lane & 1)) xq[((int64_t)(t0 + f) * nblk + blockIdx.x) * kQuantiles + (pos >> 4)] = sxv;
+    }
+    *reinterpret_cast<unsigned long long*>(perm + (int64_t)(t0 + f) * n_pad + base + lane * 8) = pm;
+}
+
 int launch_skin_fwd_sorted(const float* cano, const float* W, const float* R, const float* tr, int64_t T, int64_t N,
                            int64_t P, float* out, float* out_packed, unsigned char* perm, float* xq, int64_t n_pad,
                            cudaStream_t stream) {
@@ -156,6 +262,14 @@ int launch_skin_fwd_sorted(const float* cano, const float* W, const float* R, co
     if (P <= 0 || P > 32 || n_pad % kSortBlock != 0 || n_pad < N) return kErrUnsupported;
     int fpb = kSkinFramesPerBlock;
     while (fpb > 1 && (n_pad / kSortBlock) * ceil_div(T, fpb) < 2 * 148) fpb /= 2;
+    if (fpb == kSortFrames) {                                   // enough frames to give every warp of a CTA one to sort
+        dim3 grid8((unsigned)(n_pad / kSortBlock), (unsigned)ceil_div(T, kSortFrames));
+        const size_t smem8 = ((size_t)kSortFrames * 3 * kSortBlock + (size_t)kSortFrames * P * 12) * sizeof(float);
+        skin_fwd_sorted8_kernel<<<grid8, kSortBlock, smem8, stream>>>(cano, W, R, tr, (int)T, (int)N, (int)P, out, out_packed,
+                                                                      perm, xq, (int)n_pad);
+        REART_CHECK_LAUNCH();
+        return kOk;
+    }
     dim3 grid((unsigned)(n_pad / kSortBlock), (unsigned)ceil_div(T, fpb));
     const size_t smem = (size_t)kSortBlock * (8 + 12) + (size_t)fpb * P * 12 * sizeof(float);
     skin_fwd_sorted_kernel<<<grid, kSortBlock, smem, stream>>>(cano, W, R, tr, (int)T, (int)N, (int)P, out, out_packed,

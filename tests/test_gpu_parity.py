@@ -658,7 +658,8 @@ def test_fused_producer_energy_is_bit_identical_to_the_pipelined_one():
     from reart_b200 import _lib, ops
     L = _lib.lib()
     rng = np.random.default_rng(77)
-    for T, N, M, P in ((3, 3001, 2777, 6), (2, 4096, 4096, 15), (9, 2048 + 8, 1500, 20), (1, 777, 900, 3)):
+    # (the last shape is large enough for the pipelined side to take its 8-frames-per-CTA warp-sorted skin kernel)
+    for T, N, M, P in ((3, 3001, 2777, 6), (2, 4096, 4096, 15), (9, 2048 + 8, 1500, 20), (1, 777, 900, 3), (40, 16384 - 5, 3000, 15)):
         seq = synthetic_sequence(T, max(N, M), P, seed=11)
         cano = cu(seq["cano"][:N]); frames = cu(seq["frames"][:, :M])
         part = torch.from_numpy(seq["part"][:N].astype(np.int64)).to(dev())
