@@ -134,3 +134,23 @@ def test_engine_with_culling_follows_the_brute_force_optimisation_bit_for_bit():
     # k-d ordering permutes the points (and so the order of every float sum): same optimisation, not the same bits
     np.testing.assert_allclose(runs[True][:5], runs[False][:5], rtol=1e-5)
     np.testing.assert_allclose(runs[True], runs[False], rtol=5e-3)
+
+
+def test_engine_with_culling_at_coarse_bound_sizes_and_with_the_assignment_loss():
+    """8192 points per cloud: the history-free coarse bounds of cull.cu are active inside the engine (they cull from the
+    first step on); and culling together with the assignment loss added to Chamfer (run_real.py form) under the graph."""
+    from reart_b200.engine import RelaxationEngine, tau_schedule
+    seq = synthetic_sequence(4, 8192, 6, seed=8)
+    cano, frames = cu(seq["cano"]), cu(seq["frames"])
+    for assign in (None, dict(downsample=8, assign_gap=3, lambda_assign=0.3, assign_iter=2, mode="add")):
+        runs = {}
+        for cull in (True, False):
+            eng = RelaxationEngine(cano, frames, num_parts=6, use_graph=cull, seed=2, cull=cull, assign=assign)
+            torch.manual_seed(9)
+            runs[cull] = [float(eng.step(tau_schedule(i, 100, 5.0, 1.0))) for i in range(10)]
+            if cull:
+                ev, off = eng.culling_stats()
+                assert 0 < ev < off
+            eng.release()
+        np.testing.assert_allclose(runs[True][:4], runs[False][:4], rtol=2e-5)
+        np.testing.assert_allclose(runs[True], runs[False], rtol=5e-3)
