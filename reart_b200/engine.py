@@ -31,6 +31,14 @@ class _EngineBase:
 
     # subclasses: _iteration() -> loss tensor (local part), self.optimizer, self.bucket
     def _run_iteration(self):
+        src = getattr(self, "_ingest_src", None)
+        if src is not None:
+            # fresh clouds for this step (a caller streaming data in): device copies + re-pack as part of the iteration,
+            # i.e. inside the captured graph -- one launch per step instead of four enqueues in front of it
+            cano_src, frames_src = src
+            self.cano.copy_(cano_src)
+            self.frames.copy_(frames_src)
+            ops.pack_cloud(self.frames, out=self.frames_packed)
         if getattr(self, "native", False):
             return self._run_iteration_native()
         if getattr(self, "sink", None) is not None:
@@ -121,23 +129,41 @@ class _EngineBase:
         self._graphs = {}
         torch.cuda.synchronize()
 
-    def step(self, tau: Optional[float] = None) -> torch.Tensor:
-        """One optimisation iteration; returns the (all-rank) loss as a device tensor -- no host sync."""
+    def step(self, tau: Optional[float] = None, ingest=None) -> torch.Tensor:
+        """One optimisation iteration; returns the (all-rank) loss as a device tensor -- no host sync.
+
+        ``ingest`` = (slot, cano_src, frames_src): run the step on NEW clouds taken from the device tensors ``cano_src``
+        [N,3] / ``frames_src`` [T_local,N,3] (same shapes as the engine's; e.g. staging buffers an H2D copy just filled).
+        The copies and the re-pack are part of the captured iteration; ``slot`` (hashable) names the staging buffers, one
+        graph is captured per slot, so alternate between a fixed set of them.  Not available with ``cull=True`` (the
+        engine keeps its clouds in its own order)."""
         if tau is not None:
             self.tau.fill_(float(tau))
         self.iteration += 1
         variant = self._variant()
         self._cur_variant = variant                            # fixed for this step (warm-up and capture included)
-        if not self.use_graph:
-            out = self._run_iteration()
+        self._ingest_src = None
+        key = variant
+        if ingest is not None:
+            if getattr(self, "cull", False):
+                raise ValueError("ingest is not available with cull=True")
+            slot, cano_src, frames_src = ingest
+            assert cano_src.shape == self.cano.shape and frames_src.shape == self.frames.shape
+            self._ingest_src = (cano_src, frames_src)
+            key = (variant, "ingest", slot, cano_src.data_ptr(), frames_src.data_ptr())
+        try:
+            if not self.use_graph:
+                out = self._run_iteration()
+                self._after_replay(variant)
+                return out
+            if key not in self._graphs:
+                self._capture(key)
+            g, static_loss = self._graphs[key]
+            g.replay()
             self._after_replay(variant)
-            return out
-        if variant not in self._graphs:
-            self._capture(variant)
-        g, static_loss = self._graphs[variant]
-        g.replay()
-        self._after_replay(variant)
-        return static_loss
+            return static_loss
+        finally:
+            self._ingest_src = None
 
     def _after_replay(self, variant):
         pass

@@ -22,13 +22,17 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------- packed clouds
-def pack_cloud(pts: torch.Tensor) -> torch.Tensor:
-    """[B,P,3] -> packed float buffer for the searches (include/reart_b200.h: reart_pack_cloud)."""
+def pack_cloud(pts: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """[B,P,3] -> packed float buffer for the searches (include/reart_b200.h: reart_pack_cloud); ``out``: write into an
+    existing packed buffer of the same shape (e.g. the engine's, when new frames arrive)."""
     _lib.require_cuda(pts)
     L = _lib.lib()
     pts = _f32c(pts)
     B, P, _ = pts.shape
-    out = torch.empty(L.reart_packed_bytes(B, P) // 4, dtype=torch.float32, device=pts.device)
+    n = L.reart_packed_bytes(B, P) // 4
+    if out is None:
+        out = torch.empty(n, dtype=torch.float32, device=pts.device)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == n and out.device == pts.device
     with torch.cuda.device(pts.device):
         check(L.reart_pack_cloud(ptr(pts), B, P, ptr(out), stream_ptr()), "reart_pack_cloud")
     return out

@@ -711,6 +711,31 @@ def test_engine_with_fused_producer_follows_the_default_optimisation_bit_for_bit
         assert torch.equal(runs[key][1], ref[1]) and torch.equal(runs[key][2], ref[2]), key
 
 
+def test_engine_step_with_ingest_equals_copying_the_clouds_first():
+    """engine.step(ingest=(slot, cano_src, frames_src)) -- device copies + re-pack inside the captured iteration -- takes the
+    same steps as writing the clouds into the engine by hand before a plain step (bit for bit), alternating two slots."""
+    from reart_b200 import ops
+    from reart_b200.engine import RelaxationEngine, tau_schedule
+    seqs = [synthetic_sequence(4, 3000, 5, seed=s) for s in (3, 4)]
+    stage = [(cu(q["cano"]), cu(q["frames"])) for q in seqs]
+    runs = {}
+    for mode in ("manual_eager", "ingest_eager", "ingest_graph"):
+        eng = RelaxationEngine(stage[0][0].clone(), stage[0][1].clone(), num_parts=5, use_graph=(mode == "ingest_graph"), seed=2)
+        torch.manual_seed(9)
+        losses = []
+        for i in range(8):
+            c, f = stage[i & 1]
+            if mode == "manual_eager":
+                eng.cano.copy_(c); eng.frames.copy_(f); eng.frames_packed.copy_(ops.pack_cloud(eng.frames))
+                losses.append(float(eng.step(tau_schedule(i, 100, 5.0, 1.0))))
+            else:
+                losses.append(float(eng.step(tau_schedule(i, 100, 5.0, 1.0), ingest=(i & 1, c, f))))
+        runs[mode] = (losses, eng.model.proposal_t.detach().clone())
+        eng.release()
+    assert runs["ingest_eager"][0] == runs["manual_eager"][0] and torch.equal(runs["ingest_eager"][1], runs["manual_eager"][1])
+    assert runs["ingest_graph"][0] == runs["manual_eager"][0] and torch.equal(runs["ingest_graph"][1], runs["manual_eager"][1])
+
+
 def test_kinematic_engine_recovers_joint_angles_on_a_synthetic_tree():
     """--model=kinematic (networks/model.py:73-166): revolute chain with known screws; start from perturbed
     angles and check the fused FK + skin + Chamfer iteration drives the energy down."""
