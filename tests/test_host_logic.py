@@ -325,3 +325,27 @@ def test_bench_reference_arm_contract_on_cpu():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["dtype"] == "f32" and d["data"] == "synthetic"
+
+
+def test_kd_order_is_a_permutation_and_refining_it_keeps_the_coarse_blocks():
+    """ops.kd_order (pure torch, runs on the CPU too): a permutation; the engine orders the canonical cloud with leaf 8 but the
+    search works on blocks of 256 rows -- refining the order must leave every 256-block the same SET of points as the leaf-256
+    order (only their order inside the block changes), and make runs of 8 much tighter."""
+    from reart_b200 import ops
+    torch.manual_seed(0)
+    for N in (16384, 5000, 3001):
+        pts = torch.rand(2, N, 3)
+        coarse, fine = ops.kd_order(pts, 256), ops.kd_order(pts, 8)
+        for perm in (coarse, fine):
+            assert all(sorted(perm[i].tolist()) == list(range(N)) for i in range(2))
+        for i in range(2):
+            for blk in range(0, N - 255, 256):
+                assert set(coarse[i, blk:blk + 256].tolist()) == set(fine[i, blk:blk + 256].tolist())
+
+        def spread(perm, chunk):
+            q = torch.gather(pts, 1, perm[:, :, None].expand(-1, -1, 3))
+            n = (N // chunk) * chunk
+            c = q[:, :n].reshape(2, -1, chunk, 3)
+            return float((c.amax(2) - c.amin(2)).norm(dim=-1).mean())
+        assert spread(fine, 8) < 0.5 * spread(coarse, 8)
+        assert spread(coarse, 256) < 0.6 * spread(torch.arange(N)[None].expand(2, N), 256)
